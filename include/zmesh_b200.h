@@ -1,0 +1,148 @@
+/* zmesh_b200 -- C ABI of the B200-native multi-label marching-cubes path.
+ *
+ * This is the drop-in boundary: it replaces the C++ template the reference binds from Cython,
+ *
+ *     cdef cppclass CMesher[P, L, S]                      (reference zmesh/_zmesh.pyx:74-108)
+ *     class CMesher<PositionType, LabelType, SimplifierType>   (reference zmesh/cMesher.hpp:16-308)
+ *
+ * Label width is a run-time argument (the reference instantiates 8 classes,
+ * zmesh/_zmesh.pyx:739-1033); vertex keys are always the 64-bit layout
+ * (zi_lib/zi/mesh/marching_cubes.hpp:60-74), which is unobservable in the results.
+ * Plain pointers and sizes only; every function returns a zm_status (0 = ok) unless noted, and
+ * zm_last_error() gives the text.  A handle is not thread-safe (neither is the reference).
+ *
+ * There is no CPU fallback: every entry point that computes runs CUDA kernels built for sm_100a
+ * and fails with ZM_ERR_CUDA when no such device is usable.
+ */
+#ifndef ZMESH_B200_H
+#define ZMESH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zm_handle zm_handle;
+
+typedef enum {
+  ZM_OK = 0,
+  ZM_ERR_INVALID = 1,     /* bad argument                                   */
+  ZM_ERR_CUDA = 2,        /* CUDA runtime/driver failure (text in last_error) */
+  ZM_ERR_OOM = 3,         /* device or pinned-host allocation failed        */
+  ZM_ERR_UNSUPPORTED = 4, /* e.g. > 2^32-1 vertices in one call             */
+  ZM_ERR_STATE = 5        /* call order (get before mesh, ...)              */
+} zm_status;
+
+enum { ZM_MEM_HOST = 0, ZM_MEM_DEVICE = 1 };
+
+/* Replaces CMesher(const std::vector<float>& voxelresolution) (cMesher.hpp:24-26) and
+ * Mesher.__init__ (zmesh/_zmesh.pyx:442-444).  `resolution` is captured here, as the reference
+ * captures it when Mesher.mesh() constructs the C++ object (zmesh/_zmesh.pyx:494).
+ * device < 0 selects the current CUDA device. */
+int zm_create(const float resolution[3], int device, zm_handle** out);
+void zm_destroy(zm_handle* h);
+
+/* Replaces the resolution captured by `MesherClass(self.voxel_res)` in Mesher.mesh
+ * (zmesh/_zmesh.pyx:494): call before zm_mesh to re-capture. */
+int zm_set_resolution(zm_handle* h, const float resolution[3]);
+
+/* Replaces CMesher::mesh(const L* data, sx, sy, sz, c_order) (cMesher.hpp:29-36 ->
+ * marching_cubes::marche, zi_lib/zi/mesh/marching_cubes.hpp:291-445, 644-656) together with the
+ * `close` zero padding of Mesher.mesh (zmesh/_zmesh.pyx:502-506), which is applied virtually on
+ * the device (out-of-range voxels read as 0, coordinates shifted by +1 voxel like the padded copy).
+ *   labels       dense volume, logical shape (sx, sy, sz); element (x,y,z) at
+ *                z + sz*(y + sy*x) if c_order else x + sx*(y + sy*z); borrowed for this call only
+ *   label_bytes  1, 2, 4 or 8 (values are compared as unsigned bit patterns of that width)
+ *   mem_kind     ZM_MEM_HOST (pageable or pinned) or ZM_MEM_DEVICE (pointer on the handle's device)
+ * Previous results of the handle are dropped (as Mesher.mesh deletes the old CMesher, :469). */
+int zm_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy,
+            uint64_t sz, int c_order, int close, int mem_kind);
+
+/* Same, for one shard of a larger volume: `origin` (voxels, logical x,y,z) is added to every
+ * vertex coordinate so that shards of one volume produce identical keys on shared planes
+ * (multi-GPU slab decomposition). */
+int zm_mesh_shard(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy,
+                  uint64_t sz, int c_order, int close, int mem_kind, const uint64_t origin[3]);
+
+/* Replaces CMesher::ids() (cMesher.hpp:46-54).  The reference's order is unspecified
+ * (unordered_map iteration); here ids are ascending.  Labels that produced no triangle are
+ * absent, label 0 is never meshed (marching_cubes.hpp:438). */
+uint64_t zm_num_ids(zm_handle* h); /* returns the count */
+int zm_ids(zm_handle* h, uint64_t* out, uint64_t capacity);
+
+/* Sizes for zm_get: number of vertices and faces of `label` (0, 0 if absent or erased;
+ * cf. marching_cubes::count, marching_cubes.hpp:208 and cMesher.hpp:69-74). */
+int zm_get_counts(zm_handle* h, uint64_t label, uint64_t* n_vertices, uint64_t* n_faces);
+
+/* Replaces CMesher::get_mesh(label, normals=false, simplification_factor=0, ..., transpose)
+ * -> triangles2mesh (cMesher.hpp:60-166) fused with the Python post-processing of Mesher.get /
+ * Mesher.get_mesh: compute_normals (zmesh/_zmesh.pyx:138-152 -> zmesh/chunk_mesh.hpp:345-384) and
+ * _normalize_mesh (zmesh/_zmesh.pyx:423-433):
+ *     vertex_i = fl32( fl32( fl32(res_i * k_i) [+ offset_i if voxel_centered] ) / 2 )
+ * with res = the captured resolution and offset = `centering_offset` (the reference adds the
+ * Mesher's *current* voxel_res, which may differ from the captured one); NULL = captured.
+ *   transpose  0: Mesher.get orientation; 1: legacy Mesher.get_mesh (x/z swapped, winding flipped)
+ *   vertices   caller buffer, 3*n_vertices floats;  faces: 3*n_faces uint32 (label-local indices)
+ *   normals_out  NULL, or 3*n_vertices floats (unit normals, NaN where the reference gives NaN)
+ * Vertex/face order is unspecified (as in the reference, whose order is hash-map order). */
+int zm_get(zm_handle* h, uint64_t label, int normals, int voxel_centered, int transpose,
+           const float centering_offset[3], float* vertices, uint32_t* faces, float* normals_out);
+
+/* Replaces compute_vertex_normals_from_faces (zmesh/chunk_mesh.hpp:345-384) as exposed by
+ * Mesher.compute_normals (zmesh/_zmesh.pyx:138-152, :585-590) for an arbitrary host mesh:
+ * vertices 3*n_vertices float32, faces 3*n_faces uint32 -> normals_out 3*n_vertices float32. */
+int zm_compute_normals(zm_handle* h, const float* vertices, uint64_t n_vertices, const uint32_t* faces,
+                       uint64_t n_faces, float* normals_out);
+
+/* Replaces CMesher::erase / clear (cMesher.hpp:300-307 -> marching_cubes.hpp:184-204). */
+int zm_erase(zm_handle* h, uint64_t label, int* existed);
+int zm_clear(zm_handle* h);
+
+/* ---- bulk / device-resident access (no reference counterpart; used by bench.py and by callers
+ * that keep results on the GPU) ------------------------------------------------------------- */
+
+/* Runs the final gather for ALL labels with the given options and leaves the result on the device:
+ * vertices float32 [V_total][3], faces uint32 [T_total][3] (label-local indices), optional normals
+ * float32 [V_total][3]; label i of the directory (STORAGE order, which is unspecified -- not
+ * sorted; erased labels included) owns vertex rows [voff[i], voff[i+1]) and face rows
+ * [foff[i], foff[i+1]).  With transpose != 0 the device faces keep the Mesher.get winding; the
+ * host copies (zm_get, zm_fetch_all) reverse each row to the legacy winding.  Pointers stay valid
+ * until the next zm_mesh / zm_clear / zm_destroy on this handle. */
+typedef struct {
+  uint64_t n_labels, n_vertices, n_faces;
+  const uint64_t* labels_host; /* [n_labels] storage order                   */
+  const uint64_t* voff_host;   /* [n_labels+1]                               */
+  const uint64_t* foff_host;   /* [n_labels+1]                               */
+  const float* vertices_dev;
+  const uint32_t* faces_dev;
+  const float* normals_dev; /* NULL unless requested */
+} zm_bulk_view;
+int zm_finalize(zm_handle* h, int normals, int voxel_centered, int transpose,
+                const float centering_offset[3], zm_bulk_view* view);
+
+/* Copies the finalized arrays of all labels to host buffers in one transfer each
+ * (vertices 3*V_total floats, faces 3*T_total uint32, normals 3*V_total floats or NULL). */
+int zm_fetch_all(zm_handle* h, float* vertices, uint32_t* faces, float* normals_out);
+
+typedef struct {
+  uint64_t n_voxels, n_labels, n_vertices, n_faces;
+  uint64_t hash_capacity, perm_capacity;
+  uint32_t attempts;   /* classification passes run (1 unless a capacity guess was too small) */
+  uint32_t launches;   /* kernels launched by the last zm_mesh                                 */
+  float ms_h2d, ms_classify, ms_scan, ms_emit, ms_total; /* CUDA-event times of the last zm_mesh */
+  float ms_finalize;   /* last zm_finalize                                                     */
+  uint32_t launches_finalize;
+} zm_stats_t;
+int zm_stats(zm_handle* h, zm_stats_t* out);
+
+/* Blocks until all work queued by this handle has finished. */
+int zm_sync(zm_handle* h);
+
+const char* zm_last_error(zm_handle* h); /* h may be NULL: error of the last failed zm_create */
+const char* zm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZMESH_B200_H */

@@ -1,0 +1,86 @@
+"""CPU tests: the C-ABI library builds, loads and exports every symbol include/zmesh_b200.h
+declares (no compute without a GPU), fails loudly without a device, and `Mesh` codecs work."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.conftest import ROOT
+from zmesh_b200.mesh import Mesh
+
+
+def _declared_symbols():
+  text = open(os.path.join(ROOT, "include", "zmesh_b200.h")).read()
+  text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+  return sorted(set(re.findall(r"\b(zm_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(build_all):
+  from zmesh_b200 import _lib
+  lib = _lib.load()
+  names = _declared_symbols()
+  assert len(names) >= 18
+  for n in names:
+    assert hasattr(lib, n), f"libzmesh_b200.so does not export {n}"
+    assert n in _lib.SYMBOLS, f"{n} is declared in the header but not bound in zmesh_b200/_lib.py"
+  assert b"sm_100a" in lib.zm_version()
+
+
+def test_library_has_sm100a_code(build_all):
+  import subprocess
+  from zmesh_b200 import _lib
+  out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+  assert "sm_100a" in out
+
+
+def test_no_cpu_fallback(build_all):
+  """Without a usable device zm_create must fail (never compute on the CPU)."""
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("a GPU is present")
+  from zmesh_b200 import Mesher
+  with pytest.raises(RuntimeError, match="no CPU fallback"):
+    Mesher((1, 1, 1))
+
+
+def test_product_never_imports_oracle():
+  pkg = os.path.join(ROOT, "zmesh_b200")
+  for dirpath, _, files in os.walk(pkg):
+    for f in files:
+      if f.endswith((".py", ".cu", ".cuh", ".h")):
+        assert "oracle" not in open(os.path.join(dirpath, f)).read().lower().replace("no cpu fallback", ""), f
+
+
+def _box_mesh():
+  v = np.array([[0, 0, 0], [2, 0, 0], [0, 2, 0], [0, 0, 40], [2, 2, 40]], dtype=np.float32)
+  f = np.array([[0, 1, 2], [0, 2, 3], [1, 4, 2]], dtype=np.uint32)
+  return Mesh(v, f, None, id=7)
+
+
+def test_mesh_container():
+  m = _box_mesh()
+  assert len(m) == 5 and not m.empty() and m.segid == 7
+  assert m.vertices.dtype == np.float32 and m.faces.dtype == np.uint32
+  e = Mesh()
+  assert e.empty() and e.vertices.shape == (0, 3) and e.faces.shape == (0, 3) and e.normals is None
+  c = m.clone()
+  assert c == m
+  c.vertices[0, 0] = 1
+  assert c != m
+  cat = Mesh.concatenate(m, m)
+  assert len(cat) == 10 and cat.faces.max() == 9
+  assert m.triangles().shape == (3, 3, 3)
+
+
+def test_mesh_codecs_roundtrip():
+  m = _box_mesh()
+  assert Mesh.from_precomputed(m.to_precomputed()) == m
+  assert Mesh.from_ply(m.to_ply()) == m
+  assert Mesh.from_obj(m.to_obj()) == m
+  with_normals = m.clone()
+  with_normals.normals = np.ones((5, 3), dtype=np.float32)
+  assert Mesh.from_precomputed(with_normals.to_precomputed()) != with_normals  # normals are not stored
+  with pytest.raises(ValueError):
+    Mesh.from_precomputed(m.to_precomputed()[:20])

@@ -1,0 +1,92 @@
+"""CPU tests pinning the oracle (oracle/zmesh_oracle.c) to the reference:
+   (a) the reference's own golden PLY meshes, (b) outputs of the unmodified reference C++
+   committed as fixtures, (c) the reference shim itself when oracle/_ref is present."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import (OracleMesh, OracleMesher, assert_same_mesh, canonical_digest, have_reference,
+                           random_volume, voronoi_volume)
+from tests.cases import check_against_ref_cases
+from tests.conftest import GOLDEN
+from zmesh_b200.mesh import Mesh
+
+
+def test_port_matches_reference_fixtures(ref_cases, connectomics):
+  n = check_against_ref_cases(lambda res: OracleMesher(res, "port"), ref_cases, connectomics,
+                              assert_same_mesh, OracleMesh)
+  assert n > 100
+
+
+def test_port_matches_golden_ply_and_digests(connectomics):
+  """The reference's known-answer test (automated_test.py:215-230): legacy get_mesh at
+  res (32,32,40) equals connectomics_npy_meshes/unsimplified/<label>.ply.gz.  The port meshes a
+  crop around each label (a label's mesh only depends on its 1-voxel neighbourhood) so the CPU
+  suite stays fast; coordinates are shifted back by the crop origin."""
+  files = sorted(f for f in os.listdir(os.path.join(GOLDEN, "unsimplified")) if f.endswith(".ply.gz"))
+  assert len(files) >= 40
+  with open(os.path.join(GOLDEN, "digests_connectomics.json")) as f:
+    digests = json.load(f)["labels"]
+  vol = connectomics
+  for fn in files:
+    lbl = int(fn.split(".")[0])
+    with gzip.open(os.path.join(GOLDEN, "unsimplified", fn), "rb") as f:
+      gold = Mesh.from_ply(f.read())
+    idx = np.argwhere(vol == lbl)
+    lo = np.maximum(idx.min(axis=0) - 1, 0)
+    hi = np.minimum(idx.max(axis=0) + 2, vol.shape)
+    crop = np.asfortranarray(vol[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]])
+    m = OracleMesher((32, 32, 40), "port")
+    m.mesh(crop)
+    got = m.get_mesh(lbl)
+    # legacy vertices are (res0*z, res1*y, res2*x)/2 -> shift by the crop origin in that frame
+    got.vertices += (np.array([lo[2], lo[1], lo[0]], dtype=np.float32) * np.array([32, 32, 40], dtype=np.float32))
+    assert_same_mesh(got, OracleMesh(gold.vertices, gold.faces), what=f"golden {lbl}")
+    # and the get() orientation against the digest the unmodified reference produced
+    m4 = OracleMesher((4, 4, 40), "port")
+    m4.mesh(crop)
+    g = m4.get(lbl)
+    g.vertices += lo.astype(np.float32) * np.array([4, 4, 40], dtype=np.float32)
+    nv, nf, dig = digests[str(lbl)]
+    assert (len(g.vertices), len(g.faces)) == (nv, nf)
+    assert canonical_digest(g.vertices, g.faces) == dig, lbl
+
+
+def test_port_edge_cases():
+  m = OracleMesher((1, 1, 1), "port")
+  m.mesh(np.zeros((8, 8, 8), dtype=np.uint32))
+  assert m.ids() == []
+  m.mesh(np.full((8, 8, 8), 5, dtype=np.uint32))
+  assert m.ids() == []
+  m.mesh(np.full((3, 3, 3), 5, dtype=np.uint32), close=True)
+  assert m.ids() == [5]
+  g = m.get(5)
+  assert g.vertices.min() == 0.5 and g.vertices.max() == 3.5  # +1 voxel offset under close
+  assert m.erase(5) is True and m.erase(5) is False
+  assert len(m.get(5).vertices) == 0
+  m.mesh(np.ones((1, 5, 5), dtype=np.uint8))
+  assert m.ids() == []
+
+
+@pytest.mark.skipif(not have_reference(), reason="oracle/_ref/libzmesh_ref.so not built here")
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("close", [False, True])
+def test_port_matches_reference_shim(order, close, connectomics):
+  vols = [
+    (np.asarray(connectomics[100:164, 100:164, 100:164], order=order), (4, 4, 40)),
+    (random_volume((20, 21, 22), 30, np.uint16, seed=5, order=order), (0.1, 3.3, 7.77)),
+    (voronoi_volume((33, 30, 31), 11, np.uint64, seed=3, order=order), (4, 4, 40)),
+  ]
+  for vol, res in vols:
+    a, b = OracleMesher(res, "port"), OracleMesher(res, "reference")
+    a.mesh(vol, close=close)
+    b.mesh(vol, close=close)
+    assert sorted(a.ids()) == sorted(b.ids())
+    for lbl in a.ids():
+      for vc in (False, True):
+        assert_same_mesh(a.get(lbl, normals=True, voxel_centered=vc), b.get(lbl, normals=True, voxel_centered=vc),
+                         what=f"{lbl}")
+      assert_same_mesh(a.get_mesh(lbl, normals=True), b.get_mesh(lbl, normals=True), what=f"legacy {lbl}")

@@ -1,0 +1,288 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI via
+zmesh_b200.Mesher and is compared with the CPU oracle, the committed outputs of the unmodified
+reference, and the reference's own golden meshes.  Bit-exact for vertices/faces (canonical sets,
+SURVEY.md section 8c); normals within 1e-5 absolute (unit vectors) with equal NaN masks."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.oracle import (OracleMesh, OracleMesher, assert_same_mesh, canonical_digest, random_volume,
+                           voronoi_volume)
+from tests.cases import check_against_ref_cases
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+NORMALS_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def Mesher(build_all):
+  import zmesh_b200
+  return zmesh_b200.Mesher
+
+
+def compare_all_labels(gpu, cpu, normals=True, vcs=(False, True), legacy=False):
+  assert gpu.ids() == sorted(cpu.ids())
+  for lbl in gpu.ids():
+    for vc in vcs:
+      assert_same_mesh(gpu.get(lbl, normals=normals, voxel_centered=vc),
+                       cpu.get(lbl, normals=normals, voxel_centered=vc), NORMALS_TOL, what=f"label {lbl} vc={vc}")
+    if legacy:
+      assert_same_mesh(gpu.get_mesh(lbl, normals=normals), cpu.get_mesh(lbl, normals=normals), NORMALS_TOL,
+                       what=f"legacy {lbl}")
+  return len(gpu.ids())
+
+
+def test_reference_fixture_cases(Mesher, ref_cases, connectomics):
+  """Outputs of the unmodified reference (tests/golden/ref_cases.npz): dtype x order x close x
+  voxel_centered, anisotropic non-integer resolution, int32 negative labels, degenerate shapes."""
+  from zmesh_b200 import Mesh
+  n = check_against_ref_cases(lambda res: Mesher(res), ref_cases, connectomics,
+                              lambda g, w, what: assert_same_mesh(g, w, NORMALS_TOL, what), Mesh)
+  assert n > 100
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64])
+@pytest.mark.parametrize("close", [False, True])
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_executes(Mesher, dtype, close, order):
+  """The reference's smoke test (automated_test.py:43-61 and :22-40), run against the drop-in."""
+  labels = np.zeros((11, 17, 19), dtype=dtype, order=order)
+  labels[1:-1, 1:-1, 1:-1] = 1
+  mesher = Mesher((4, 4, 40))
+  mesher.mesh(labels, close=close)
+  for getter in (mesher.get, mesher.get_mesh):
+    mesh = getter(1, normals=False)
+    assert len(mesh.vertices) > 0 and len(mesh.faces) > 0 and mesh.normals is None
+    mesh = getter(1, normals=True)
+    assert len(mesh.vertices) > 0 and len(mesh.faces) > 0 and len(mesh.normals) > 0
+    assert mesh.normals.dtype == np.float64 and mesh.vertices.dtype == np.float32 and mesh.faces.dtype == np.uint32
+
+
+def test_codecs_roundtrip_on_gpu_mesh(Mesher):
+  """automated_test.py:127-170 (precomputed / obj / ply)."""
+  from zmesh_b200 import Mesh
+  labels = np.zeros((11, 17, 19), dtype=np.uint32)
+  labels[1:-1, 1:-1, 1:-1] = 1
+  mesher = Mesher((4, 4, 40))
+  mesher.mesh(labels)
+  mesh = mesher.get(1, normals=False)
+  assert Mesh.from_precomputed(mesh.to_precomputed()) == mesh
+  assert Mesh.from_obj(mesh.to_obj()) == mesh
+  assert Mesh.from_ply(mesh.to_ply()) == mesh
+  assert Mesh.from_precomputed(mesher.get(1, normals=True).to_precomputed()) != mesher.get(1, normals=True)
+
+
+SEEDED = [
+  # name, volume factory, res, close
+  ("crop128_F", lambda c: np.asfortranarray(c[100:228, 100:228, 100:228]), (4, 4, 40), False),
+  ("crop_C_close_odd", lambda c: np.ascontiguousarray(c[37:140, 250:331, 400:467]), (0.1, 3.3, 7.77), True),
+  ("random64_u32_C", lambda c: random_volume((64, 64, 64), 1000, np.uint32, 0, "C"), (4, 4, 40), False),
+  ("random40_u16_F_close", lambda c: random_volume((40, 41, 43), 300, np.uint16, 1, "F"), (1, 1, 1), True),
+  ("random33_u8", lambda c: random_volume((33, 34, 35), 4, np.uint8, 2, "C"), (2, 3, 5), True),
+  ("voronoi_u64_F_close", lambda c: voronoi_volume((100, 90, 80), 24, np.uint64, 0, "F"), (4, 4, 40), True),
+  ("voronoi_u64_C", lambda c: voronoi_volume((70, 65, 97), 16, np.uint64, 1, "C"), (4, 4, 40), False),
+  ("thin_f", lambda c: random_volume((2, 50, 60), 5, np.uint32, 3, "F"), (1, 1, 1), False),
+  ("thin_s", lambda c: random_volume((70, 40, 2), 5, np.uint32, 4, "F"), (1, 1, 1), True),
+  ("tile_edges", lambda c: random_volume((33, 9, 9), 3, np.uint8, 5, "F"), (1, 1, 1), False),
+  ("tile_exact", lambda c: random_volume((64, 16, 16), 7, np.uint16, 6, "F"), (1, 1, 1), False),
+]
+
+
+@pytest.mark.parametrize("case", SEEDED, ids=[c[0] for c in SEEDED])
+def test_seeded_volumes_match_oracle(Mesher, connectomics, case):
+  name, make, res, close = case
+  vol = make(connectomics)
+  gpu, cpu = Mesher(res), OracleMesher(res, "port")
+  gpu.mesh(vol, close=close)
+  cpu.mesh(vol, close=close)
+  n = compare_all_labels(gpu, cpu, normals=True, legacy=(name in ("crop128_F", "random33_u8")))
+  assert n > 0
+
+
+def test_many_labels_table_growth(Mesher):
+  """Every voxel its own label: > 2^16 labels forces the global label table to grow, and the
+  CTA-local table overflows into the direct global path."""
+  vol = (np.arange(48 * 48 * 40, dtype=np.uint32) + 1).reshape((48, 48, 40))
+  rng = np.random.default_rng(0)
+  vol = rng.permutation(vol.ravel()).reshape(vol.shape).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+  gpu, cpu = Mesher((1, 1, 1)), OracleMesher((1, 1, 1), "port")
+  gpu.mesh(vol)
+  cpu.mesh(vol)
+  assert gpu.stats()["attempts"] > 1
+  ids = gpu.ids()
+  assert ids == sorted(cpu.ids()) and len(ids) == vol.size
+  for lbl in ids[::997]:
+    assert_same_mesh(gpu.get(lbl, normals=True), cpu.get(lbl, normals=True), NORMALS_TOL, what=str(lbl))
+
+
+def test_api_semantics(Mesher):
+  vol = np.zeros((20, 20, 20), dtype=np.uint16)
+  vol[2:8, 2:8, 2:8] = 300
+  vol[10:15, 3:9, 4:12] = 7
+  m = Mesher((4, 4, 40))
+  m.mesh(vol)
+  assert m.ids() == [7, 300]
+  missing = m.get(12345)
+  assert missing.vertices.shape == (0, 3) and missing.faces.shape == (0, 3) and missing.id == 12345
+  with pytest.raises(OverflowError):
+    m.get(1 << 20)  # does not fit uint16 (the reference raises the same)
+  with pytest.raises(NotImplementedError):
+    m.get(7, reduction_factor=10)
+  assert m.erase(7) is True and m.erase(7) is False
+  assert m.ids() == [300] and len(m.get(7).vertices) == 0
+  # captured resolution vs current voxel_res (zmesh/_zmesh.pyx:494 vs :581)
+  m.voxel_res = (1, 1, 1)
+  a = m.get(300, voxel_centered=True)
+  ref = OracleMesher((4, 4, 40), "port")
+  ref.mesh(vol)
+  ref.voxel_res = (1, 1, 1)
+  assert_same_mesh(a, ref.get(300, voxel_centered=True), what="captured res")
+  m.clear()
+  assert m.ids() == [] and len(m.get(300).vertices) == 0
+  # remeshing with the same handle
+  m.voxel_res = (2, 2, 2)
+  m.mesh(vol, close=True)
+  assert m.ids() == [7, 300]
+  with pytest.raises(IndexError):
+    m.mesh(np.zeros((4, 4), dtype=np.uint8))
+  # compute_normals on an arbitrary mesh
+  g = m.get(300)
+  cn = m.compute_normals(g.clone())
+  want = ref.compute_normals(g.vertices, g.faces)
+  assert np.allclose(cn.normals, want, atol=NORMALS_TOL, equal_nan=True)
+
+
+def test_non_contiguous_and_4d_input(Mesher, connectomics):
+  base = np.ascontiguousarray(connectomics[50:114, 60:100, 70:118])
+  strided = base[::2, :, ::3]
+  assert not strided.flags.c_contiguous and not strided.flags.f_contiguous
+  gpu, cpu = Mesher((4, 4, 40)), OracleMesher((4, 4, 40), "port")
+  gpu.mesh(strided)
+  cpu.mesh(strided)
+  compare_all_labels(gpu, cpu, normals=False, vcs=(False,))
+  four_d = np.asfortranarray(base)[..., None]
+  gpu.mesh(four_d)
+  cpu.mesh(np.asfortranarray(base))
+  compare_all_labels(gpu, cpu, normals=False, vcs=(False,))
+  b = (base % 2).astype(bool)
+  gpu.mesh(b)
+  cpu.mesh(b)
+  compare_all_labels(gpu, cpu, normals=False, vcs=(False,))
+
+
+def test_device_input(Mesher):
+  import torch
+  vol = voronoi_volume((64, 48, 40), 16, np.uint64, seed=2, order="C")
+  t = torch.from_numpy(vol.view(np.int64)).cuda()
+  gpu, cpu = Mesher((4, 4, 40)), OracleMesher((4, 4, 40), "port")
+  gpu.mesh(t, close=True)
+  cpu.mesh(vol, close=True)
+  compare_all_labels(gpu, cpu, normals=True, vcs=(True,))
+
+
+def test_c_and_f_order_give_identical_sets(Mesher, connectomics):
+  """automated_test.py:172-193 strengthened to canonical equality."""
+  crop = connectomics[102:230, 31:159, 17:145]
+  f, c = Mesher((1, 1, 1)), Mesher((1, 1, 1))
+  f.mesh(np.asfortranarray(crop))
+  c.mesh(np.ascontiguousarray(crop))
+  assert f.ids() == c.ids()
+  for lbl in f.ids():
+    assert_same_mesh(f.get(lbl), c.get(lbl), what=str(lbl))
+    assert_same_mesh(f.get_mesh(lbl), c.get_mesh(lbl), what=f"legacy {lbl}")
+
+
+def test_degenerate_volumes_512(Mesher):
+  """BASELINE config 2: all-zero and single-label 512^3 uint32."""
+  m = Mesher((4, 4, 40))
+  m.mesh(np.zeros((512, 512, 512), dtype=np.uint32))
+  assert m.ids() == []
+  ones = np.ones((512, 512, 512), dtype=np.uint32)
+  m.mesh(ones)
+  assert m.ids() == []
+  m.mesh(ones, close=True)
+  assert m.ids() == [1]
+  g = m.get(1)
+  assert (len(g.vertices), len(g.faces)) == (1572864, 3145724)  # SURVEY.md section 6 probe of the reference
+  # closed surface: every undirected edge is used by exactly two faces, and V - E + F = 2
+  e = np.sort(np.concatenate([g.faces[:, [0, 1]], g.faces[:, [1, 2]], g.faces[:, [2, 0]]]).astype(np.uint64), axis=1)
+  ek = e[:, 0] << np.uint64(32) | e[:, 1]
+  uniq, cnt = np.unique(ek, return_counts=True)
+  assert (cnt == 2).all()
+  assert len(g.vertices) - len(uniq) + len(g.faces) == 2
+  assert g.vertices.min() == 2.0 and g.vertices[:, 2].max() == 513.0 * 20
+
+
+def test_connectomics_full_against_reference_digests(Mesher, connectomics):
+  """BASELINE config 1 at full size: all 2523 labels, canonical sha256 equal to what the
+  unmodified reference produced (tests/golden/digests_connectomics.json), plus the census."""
+  with open(os.path.join(GOLDEN, "digests_connectomics.json")) as f:
+    golden = json.load(f)
+  m = Mesher(tuple(golden["res"]))
+  m.mesh(connectomics, close=False)
+  ids = m.ids()
+  assert [str(i) for i in ids] == sorted(golden["labels"].keys(), key=int)
+  st = m.stats()
+  assert (st["n_vertices"], st["n_faces"]) == (44969925, 89540172)
+  bulk = m.finalize()
+  v, f, _ = m.fetch_all()
+  order = np.argsort(bulk["labels"])
+  for i in order:
+    lbl = int(bulk["labels"][i])
+    nv, nf, dig = golden["labels"][str(lbl)]
+    vv = v[bulk["voff"][i]:bulk["voff"][i + 1]]
+    ff = f[bulk["foff"][i]:bulk["foff"][i + 1]]
+    assert (len(vv), len(ff)) == (nv, nf), lbl
+    assert canonical_digest(vv, ff) == dig, lbl
+  # the per-label accessor returns the same arrays as the bulk path
+  for lbl in ids[:5] + ids[-5:]:
+    g = m.get(lbl)
+    assert canonical_digest(g.vertices, g.faces) == golden["labels"][str(lbl)][2]
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+def test_golden_ply_meshes(Mesher, connectomics, order):
+  """The reference's known-answer test (automated_test.py:215-230) on the committed subset of
+  connectomics_npy_meshes/unsimplified, with the strong canonical form instead of a column sort."""
+  from zmesh_b200 import Mesh
+  vol = np.asarray(connectomics, order=order)
+  m = Mesher((32, 32, 40))
+  m.mesh(vol)
+  files = sorted(f for f in os.listdir(os.path.join(GOLDEN, "unsimplified")) if f.endswith(".ply.gz"))
+  for fn in files:
+    lbl = int(fn.split(".")[0])
+    with gzip.open(os.path.join(GOLDEN, "unsimplified", fn), "rb") as f:
+      gold = Mesh.from_ply(f.read())
+    got = m.get_mesh(lbl, normals=False, simplification_factor=0, max_simplification_error=40)
+    assert np.all(np.sort(gold.vertices[gold.faces], axis=0) == np.sort(got.vertices[got.faces], axis=0))
+    assert_same_mesh(got, OracleMesh(gold.vertices, gold.faces), what=f"golden {lbl}")
+
+
+def test_vertex_census_identity_random256(Mesher):
+  """Size-independent property at a size the oracle would take minutes for (config 3 shape,
+  256^3): V_label = number of axis-adjacent voxel pairs with exactly one endpoint == label, and
+  every face index is in range, every vertex referenced."""
+  vol = random_volume((256, 256, 256), 1000, np.uint32, seed=0, order="C")
+  m = Mesher((4, 4, 40))
+  m.mesh(vol)
+  want = np.zeros(1000, dtype=np.int64)
+  for ax in range(3):
+    a = np.moveaxis(vol, ax, 0)[:-1].ravel()
+    b = np.moveaxis(vol, ax, 0)[1:].ravel()
+    d = a != b
+    want += np.bincount(a[d], minlength=1000) + np.bincount(b[d], minlength=1000)
+  bulk = m.finalize()
+  got = dict(zip(bulk["labels"].tolist(), np.diff(bulk["voff"]).tolist()))
+  assert sorted(got) == list(range(1, 1000))
+  for lbl in range(1, 1000):
+    assert got[lbl] == want[lbl], lbl
+  v, f, _ = m.fetch_all()
+  for i in range(0, len(bulk["labels"]), 97):
+    ff = f[bulk["foff"][i]:bulk["foff"][i + 1]]
+    nv = int(bulk["voff"][i + 1] - bulk["voff"][i])
+    assert ff.max() < nv and len(np.unique(ff)) == nv

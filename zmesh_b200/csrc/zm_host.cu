@@ -1,0 +1,632 @@
+// zmesh_b200 host layer: the C ABI of include/zmesh_b200.h over the sm_100a kernels.
+//
+// Host-side counterpart of the reference's CMesher facade (zmesh/cMesher.hpp:16-308): owns the
+// per-label results on the device, orchestrates classify -> scan -> emit -> final gather on one
+// CUDA stream, and hands label ranges back to the caller.  No CPU compute path exists here.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/zmesh_b200.h"
+#include "zm_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {  // grow-only device allocation cached in the handle across calls
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct LabelRec {
+  uint64_t label, nv, nt, voff, foff;
+  bool erased;
+};
+
+struct FinalState {
+  bool valid = false;
+  int normals = 0, voxel_centered = 0, transpose = 0;
+  float off[3] = {0, 0, 0};
+};
+
+}  // namespace
+
+struct zm_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float res[3] = {1, 1, 1};
+  std::string err;
+
+  // capacity guesses carried between calls
+  uint32_t hash_cap = 1u << 16;
+  double perm_ratio = 0.25;  // perm capacity as a fraction of the voxel count
+
+  // scratch + results (device)
+  DevBuf d_vol, d_keys, d_cntV, d_cntT, d_curT, d_offV, d_offT, d_list, d_rowbase, d_perm, d_misc;
+  DevBuf d_vkeys, d_faces, d_verts, d_normals;
+  unsigned long long* h_misc = nullptr;  // pinned: totals[4], flags
+  std::vector<uint64_t> h_list;
+
+  // results (host)
+  bool has_result = false;
+  uint32_t table_cap = 0;  // capacity of the label table the result offsets refer to
+  uint64_t Vtot = 0, Ttot = 0;
+  std::vector<LabelRec> recs;                   // storage (table) order
+  std::unordered_map<uint64_t, uint32_t> index;  // label -> recs index
+  std::vector<uint64_t> sorted_ids;
+  std::vector<uint64_t> bulk_labels, bulk_voff, bulk_foff;
+  FinalState fin;
+  zm_stats_t stats{};
+};
+
+namespace {
+
+using namespace zm;
+
+#define ZM_CUDA(h, call)                                                                       \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      char _b[512];                                                                            \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      (h)->err = _b;                                                                           \
+      cudaGetLastError();                                                                      \
+      return _e == cudaErrorMemoryAllocation ? ZM_ERR_OOM : ZM_ERR_CUDA;                       \
+    }                                                                                          \
+  } while (0)
+
+int fail(zm_handle* h, int code, const std::string& msg) {
+  h->err = msg;
+  return code;
+}
+
+typedef void (*classify_fn)(const VolParams, const Pass1Args);
+typedef void (*emit_fn)(const VolParams, const Pass2Args);
+
+struct KernelSet {
+  classify_fn classify;
+  emit_fn emit;
+  size_t classify_smem, emit_smem;
+};
+
+template <typename L, bool CO>
+KernelSet make_set() {
+  return KernelSet{k_classify<L, CO>, k_emit<L, CO>, classify_smem_bytes<L>(), emit_smem_bytes<L>()};
+}
+
+KernelSet kernel_set(int label_bytes, bool c_order) {
+  switch (label_bytes) {
+    case 1: return c_order ? make_set<uint8_t, true>() : make_set<uint8_t, false>();
+    case 2: return c_order ? make_set<uint16_t, true>() : make_set<uint16_t, false>();
+    case 4: return c_order ? make_set<uint32_t, true>() : make_set<uint32_t, false>();
+    default: return c_order ? make_set<unsigned long long, true>() : make_set<unsigned long long, false>();
+  }
+}
+
+int prepare_device(zm_handle* h) {
+  // case tables -> device globals; opt in to > 48 KB of shared memory per CTA where needed
+  ZM_CUDA(h, cudaMemcpyToSymbol(TRI_COUNT_D, TRI_COUNT, sizeof(TRI_COUNT)));
+  static_assert(sizeof(TRI_NIBBLES) == 256 * sizeof(unsigned long long), "table size");
+  ZM_CUDA(h, cudaMemcpyToSymbol(TRI_NIBBLES_D, TRI_NIBBLES, sizeof(TRI_NIBBLES)));
+  for (int lb : {1, 2, 4, 8})
+    for (int co = 0; co < 2; ++co) {
+      KernelSet ks = kernel_set(lb, co != 0);
+      ZM_CUDA(h, cudaFuncSetAttribute((const void*)ks.classify, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)ks.classify_smem));
+      ZM_CUDA(h, cudaFuncSetAttribute((const void*)ks.emit, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)ks.emit_smem));
+    }
+  return ZM_OK;
+}
+
+void drop_results(zm_handle* h) {
+  h->has_result = false;
+  h->Vtot = h->Ttot = 0;
+  h->recs.clear();
+  h->index.clear();
+  h->sorted_ids.clear();
+  h->bulk_labels.clear();
+  h->bulk_voff.clear();
+  h->bulk_foff.clear();
+  h->fin = FinalState();
+}
+
+uint32_t grid_for(unsigned long long n, int block) {
+  unsigned long long g = (n + block - 1) / block;
+  const unsigned long long cap = 148ull * 16ull;
+  if (g > cap) g = cap;
+  if (g == 0) g = 1;
+  return (uint32_t)g;
+}
+
+int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz,
+             int c_order, int close, int mem_kind, const uint64_t origin[3]) {
+  if (!h) return ZM_ERR_INVALID;
+  h->err.clear();
+  drop_results(h);  // Mesher.mesh deletes the previous CMesher first (zmesh/_zmesh.pyx:469)
+  if (label_bytes != 1 && label_bytes != 2 && label_bytes != 4 && label_bytes != 8)
+    return fail(h, ZM_ERR_INVALID, "label_bytes must be 1, 2, 4 or 8");
+  if (mem_kind != ZM_MEM_HOST && mem_kind != ZM_MEM_DEVICE) return fail(h, ZM_ERR_INVALID, "bad mem_kind");
+  const uint64_t pad = close ? 1 : 0;
+  const uint64_t lim = (1ull << 20) - 4;
+  if (sx + origin[0] > lim || sy + origin[1] > lim || sz + origin[2] > lim)
+    return fail(h, ZM_ERR_UNSUPPORTED, "extent exceeds the 21-bit half-voxel key range (2^20 voxels per axis)");
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  h->stats = zm_stats_t{};
+  h->stats.n_voxels = sx * sy * sz;
+  h->has_result = true;
+  h->table_cap = 0;
+  if (sx == 0 || sy == 0 || sz == 0) return ZM_OK;
+  if (!labels) return fail(h, ZM_ERR_INVALID, "labels is NULL");
+
+  VolParams vp{};
+  if (c_order) { vp.nf = (uint32_t)sz; vp.nm = (uint32_t)sy; vp.ns = (uint32_t)sx; }
+  else         { vp.nf = (uint32_t)sx; vp.nm = (uint32_t)sy; vp.ns = (uint32_t)sz; }
+  vp.pad = (uint32_t)pad;
+  vp.Ef = vp.nf + 2 * vp.pad; vp.Em = vp.nm + 2 * vp.pad; vp.Es = vp.ns + 2 * vp.pad;
+  vp.ox = (uint32_t)origin[0]; vp.oy = (uint32_t)origin[1]; vp.oz = (uint32_t)origin[2];
+  // no cube without two voxels along every axis (marching_cubes.hpp:226-257 loops are empty)
+  if (vp.Ef < 2 || vp.Em < 2 || vp.Es < 2) return ZM_OK;
+  vp.ntf = (vp.Ef + TF - 1) / TF; vp.ntm = (vp.Em + TM - 1) / TM; vp.nts = (vp.Es + TS - 1) / TS;
+  const unsigned long long ntiles = (unsigned long long)vp.ntf * vp.ntm * vp.nts;
+  if (ntiles > 0x7FFFFFFFull) return fail(h, ZM_ERR_UNSUPPORTED, "too many tiles for one launch; shard the volume");
+  const unsigned long long nvox = (unsigned long long)vp.nf * vp.nm * vp.ns;
+  const size_t vol_bytes = (size_t)nvox * label_bytes;
+
+  cudaStream_t st = h->stream;
+  ZM_CUDA(h, cudaEventRecord(h->ev[0], st));
+  if (mem_kind == ZM_MEM_HOST) {
+    ZM_CUDA(h, h->d_vol.ensure(vol_bytes));
+    ZM_CUDA(h, cudaMemcpyAsync(h->d_vol.p, labels, vol_bytes, cudaMemcpyHostToDevice, st));
+    vp.data = h->d_vol.p;
+  } else {
+    vp.data = labels;
+  }
+  ZM_CUDA(h, cudaEventRecord(h->ev[1], st));
+
+  const KernelSet ks = kernel_set(label_bytes, c_order != 0);
+  const size_t nrows = (size_t)vp.Es * vp.Em * vp.ntf;
+  ZM_CUDA(h, h->d_rowbase.ensure(nrows * sizeof(uint32_t)));
+  ZM_CUDA(h, h->d_misc.ensure(64));
+  unsigned long long* d_totals = h->d_misc.as<unsigned long long>();      // [4]
+  unsigned long long* d_cursor = h->d_misc.as<unsigned long long>() + 4;  // [1]
+  uint32_t* d_flags = reinterpret_cast<uint32_t*>(h->d_misc.as<unsigned long long>() + 5);
+
+  unsigned long long permcap = (unsigned long long)(h->perm_ratio * (double)nvox) + 4096ull;
+  if (permcap > 0xFFFFFFF0ull) permcap = 0xFFFFFFF0ull;
+  uint32_t flags = 0;
+  unsigned long long totals[4] = {0, 0, 0, 0};
+  uint32_t launches = 0;
+  int attempt = 0;
+  for (;; ++attempt) {
+    if (attempt >= 8) return fail(h, ZM_ERR_UNSUPPORTED, "label table / perm sizing did not converge");
+    const uint32_t cap = h->hash_cap;
+    ZM_CUDA(h, h->d_keys.ensure((size_t)cap * 8));
+    ZM_CUDA(h, h->d_cntV.ensure((size_t)cap * 4));
+    ZM_CUDA(h, h->d_cntT.ensure((size_t)cap * 4));
+    ZM_CUDA(h, h->d_offV.ensure((size_t)cap * 8));
+    ZM_CUDA(h, h->d_offT.ensure((size_t)cap * 8));
+    ZM_CUDA(h, h->d_list.ensure((size_t)cap * 24));
+    ZM_CUDA(h, h->d_perm.ensure((size_t)permcap * 4));
+    ZM_CUDA(h, cudaMemsetAsync(h->d_keys.p, 0, (size_t)cap * 8, st));
+    ZM_CUDA(h, cudaMemsetAsync(h->d_cntV.p, 0, (size_t)cap * 4, st));
+    ZM_CUDA(h, cudaMemsetAsync(h->d_cntT.p, 0, (size_t)cap * 4, st));
+    ZM_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 64, st));
+
+    LabelTable ht{h->d_keys.as<unsigned long long>(), h->d_cntV.as<uint32_t>(), h->d_cntT.as<uint32_t>(), cap - 1};
+    Pass1Args p1{ht, h->d_rowbase.as<uint32_t>(), h->d_perm.as<uint32_t>(), permcap, d_cursor, d_flags};
+    ks.classify<<<(uint32_t)ntiles, NT, ks.classify_smem, st>>>(vp, p1);
+    ZM_CUDA(h, cudaGetLastError());
+    ZM_CUDA(h, cudaEventRecord(h->ev[2], st));
+    ScanOut so{h->d_offV.as<unsigned long long>(), h->d_offT.as<unsigned long long>(),
+               h->d_list.as<unsigned long long>(), d_totals};
+    k_label_scan<<<1, 1024, 0, st>>>(ht, so, d_cursor);
+    ZM_CUDA(h, cudaGetLastError());
+    launches += 2;
+    ZM_CUDA(h, cudaMemcpyAsync(h->h_misc, h->d_misc.p, 48, cudaMemcpyDeviceToHost, st));
+    ZM_CUDA(h, cudaEventRecord(h->ev[3], st));
+    ZM_CUDA(h, cudaStreamSynchronize(st));
+    memcpy(totals, h->h_misc, sizeof(totals));
+    flags = *reinterpret_cast<uint32_t*>(h->h_misc + 5);
+    if (flags & FLAG_HASH_FULL) {
+      if (h->hash_cap >= (1u << 30)) return fail(h, ZM_ERR_UNSUPPORTED, "more than 2^29 distinct labels");
+      h->hash_cap <<= 3;
+      continue;
+    }
+    // keep the table at most half full so probes stay short
+    if (totals[0] * 2 > cap) {
+      while ((unsigned long long)h->hash_cap < totals[0] * 4 && h->hash_cap < (1u << 30)) h->hash_cap <<= 1;
+      continue;
+    }
+    if (totals[3] > 0xFFFFFFF0ull || (flags & FLAG_RANK_OVERFLOW))
+      return fail(h, ZM_ERR_UNSUPPORTED, "more than 2^32-16 vertices in one call; shard the volume");
+    if (flags & FLAG_PERM_FULL) {
+      permcap = totals[3] + 4096ull;
+      h->perm_ratio = std::max(h->perm_ratio, 1.05 * (double)totals[3] / (double)nvox);
+      continue;
+    }
+    break;
+  }
+  h->stats.attempts = (uint32_t)attempt + 1;
+  const uint32_t cap = h->hash_cap;
+  const unsigned long long nlabels = totals[0], Vtot = totals[1], Ttot = totals[2];
+  if (Vtot != totals[3]) return fail(h, ZM_ERR_CUDA, "internal: vertex totals disagree");
+
+  ZM_CUDA(h, cudaEventRecord(h->ev[3], st));
+  if (nlabels) {
+    ZM_CUDA(h, h->d_vkeys.ensure((size_t)Vtot * 8));
+    ZM_CUDA(h, h->d_faces.ensure((size_t)Ttot * 12));
+    ZM_CUDA(h, h->d_curT.ensure((size_t)cap * 4));
+    ZM_CUDA(h, cudaMemsetAsync(h->d_curT.p, 0, (size_t)cap * 4, st));
+    LabelTable ht{h->d_keys.as<unsigned long long>(), h->d_cntV.as<uint32_t>(), h->d_cntT.as<uint32_t>(), cap - 1};
+    Pass2Args p2{ht, h->d_offV.as<unsigned long long>(), h->d_offT.as<unsigned long long>(),
+                 h->d_curT.as<uint32_t>(), h->d_rowbase.as<uint32_t>(), h->d_perm.as<uint32_t>(),
+                 h->d_vkeys.as<unsigned long long>(), h->d_faces.as<uint32_t>(), d_flags};
+    ks.emit<<<(uint32_t)ntiles, NT, ks.emit_smem, st>>>(vp, p2);
+    ZM_CUDA(h, cudaGetLastError());
+    launches += 1;
+    h->h_list.resize((size_t)nlabels * 3);
+    ZM_CUDA(h, cudaMemcpyAsync(h->h_list.data(), h->d_list.p, (size_t)nlabels * 24, cudaMemcpyDeviceToHost, st));
+    ZM_CUDA(h, cudaMemcpyAsync(h->h_misc, h->d_misc.p, 48, cudaMemcpyDeviceToHost, st));
+  }
+  ZM_CUDA(h, cudaEventRecord(h->ev[4], st));
+  ZM_CUDA(h, cudaStreamSynchronize(st));
+  if (nlabels) {
+    flags = *reinterpret_cast<uint32_t*>(h->h_misc + 5);
+    if (flags & FLAG_INTERNAL) return fail(h, ZM_ERR_CUDA, "internal: label missing from the table in the emit pass");
+  }
+
+  // host-side label directory (storage order = table order; offsets are running sums)
+  h->recs.resize((size_t)nlabels);
+  h->index.reserve((size_t)nlabels * 2);
+  uint64_t vo = 0, fo = 0;
+  for (size_t i = 0; i < (size_t)nlabels; ++i) {
+    LabelRec& r = h->recs[i];
+    r.label = h->h_list[3 * i];
+    r.nv = h->h_list[3 * i + 1];
+    r.nt = h->h_list[3 * i + 2];
+    r.voff = vo;
+    r.foff = fo;
+    r.erased = false;
+    vo += r.nv;
+    fo += r.nt;
+    h->index.emplace(r.label, (uint32_t)i);
+  }
+  if (vo != Vtot || fo != Ttot) return fail(h, ZM_ERR_CUDA, "internal: label directory does not add up");
+  h->sorted_ids.reserve((size_t)nlabels);
+  for (const LabelRec& r : h->recs)
+    if (r.nt) h->sorted_ids.push_back(r.label);
+  std::sort(h->sorted_ids.begin(), h->sorted_ids.end());
+  h->Vtot = Vtot;
+  h->Ttot = Ttot;
+  h->table_cap = cap;
+
+  h->stats.n_labels = h->sorted_ids.size();
+  h->stats.n_vertices = Vtot;
+  h->stats.n_faces = Ttot;
+  h->stats.hash_capacity = cap;
+  h->stats.perm_capacity = permcap;
+  h->stats.launches = launches;
+  cudaEventElapsedTime(&h->stats.ms_h2d, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&h->stats.ms_classify, h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&h->stats.ms_scan, h->ev[2], h->ev[3]);
+  cudaEventElapsedTime(&h->stats.ms_emit, h->ev[3], h->ev[4]);
+  cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[4]);
+  // let the perm guess track the data (next call of a similar volume needs one attempt)
+  h->perm_ratio = std::max(0.02, std::min(6.5, 1.25 * (double)Vtot / (double)nvox));
+  return ZM_OK;
+}
+
+int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, const float* off) {
+  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  float o[3] = {h->res[0], h->res[1], h->res[2]};
+  if (off) { o[0] = off[0]; o[1] = off[1]; o[2] = off[2]; }
+  normals = normals ? 1 : 0; voxel_centered = voxel_centered ? 1 : 0; transpose = transpose ? 1 : 0;
+  FinalState& f = h->fin;
+  const bool same_verts = f.valid && f.voxel_centered == voxel_centered && f.transpose == transpose &&
+                          (!voxel_centered || (f.off[0] == o[0] && f.off[1] == o[1] && f.off[2] == o[2]));
+  const bool need_normals = normals && !(same_verts && f.normals);
+  if (same_verts && !need_normals) return ZM_OK;
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  uint32_t launches = 0;
+  ZM_CUDA(h, cudaEventRecord(h->ev[0], st));
+  if (h->Vtot) {
+    if (!same_verts) {
+      ZM_CUDA(h, h->d_verts.ensure((size_t)h->Vtot * 12));
+      FinalizeArgs fa{h->d_vkeys.as<unsigned long long>(), h->d_verts.as<float>(), h->Vtot,
+                      h->res[0], h->res[1], h->res[2], o[0], o[1], o[2], voxel_centered, transpose};
+      k_finalize_vertices<<<grid_for(h->Vtot, 256), 256, 0, st>>>(fa);
+      ZM_CUDA(h, cudaGetLastError());
+      ++launches;
+    }
+    if (need_normals) {
+      ZM_CUDA(h, h->d_normals.ensure((size_t)h->Vtot * 12));
+      ZM_CUDA(h, cudaMemsetAsync(h->d_normals.p, 0, (size_t)h->Vtot * 12, st));
+      NormalsArgs na{h->d_vkeys.as<unsigned long long>(), h->d_faces.as<uint32_t>(), h->d_normals.as<float>(),
+                     h->d_offV.as<unsigned long long>(), h->d_offT.as<unsigned long long>(), h->Ttot, h->Vtot,
+                     h->table_cap, h->res[0], h->res[1], h->res[2], transpose};
+      k_normals_accumulate<<<grid_for(h->Ttot, 256), 256, 0, st>>>(na);
+      ZM_CUDA(h, cudaGetLastError());
+      k_normals_normalize<<<grid_for(h->Vtot, 256), 256, 0, st>>>(h->d_normals.as<float>(), h->Vtot);
+      ZM_CUDA(h, cudaGetLastError());
+      launches += 2;
+    }
+  }
+  ZM_CUDA(h, cudaEventRecord(h->ev[1], st));
+  ZM_CUDA(h, cudaStreamSynchronize(st));
+  cudaEventElapsedTime(&h->stats.ms_finalize, h->ev[0], h->ev[1]);
+  h->stats.launches_finalize = launches;
+  const bool had_normals = same_verts && f.normals;
+  f.valid = true;
+  f.voxel_centered = voxel_centered;
+  f.transpose = transpose;
+  f.off[0] = o[0]; f.off[1] = o[1]; f.off[2] = o[2];
+  f.normals = (normals || had_normals) ? 1 : 0;
+  return ZM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* zm_version(void) { return "zmesh_b200 0.1 (sm_100a)"; }
+
+const char* zm_last_error(zm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int zm_create(const float resolution[3], int device, zm_handle** out) {
+  if (!out || !resolution) { g_create_error = "null argument"; return ZM_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no usable CUDA device: ") + cudaGetErrorString(e) +
+                     " (zmesh_b200 has no CPU fallback)";
+    cudaGetLastError();
+    return ZM_ERR_CUDA;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= ndev) { g_create_error = "device index out of range"; return ZM_ERR_INVALID; }
+  zm_handle* h = new zm_handle();
+  h->device = device;
+  for (int i = 0; i < 3; ++i) h->res[i] = resolution[i];
+  auto bail = [&](const char* what, cudaError_t err) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    cudaGetLastError();
+    delete h;
+    return ZM_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (auto& ev : h->ev)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if ((e = cudaHostAlloc((void**)&h->h_misc, 64, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  int rc = prepare_device(h);
+  if (rc != ZM_OK) {
+    g_create_error = h->err;
+    zm_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return ZM_OK;
+}
+
+void zm_destroy(zm_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (DevBuf* b : {&h->d_vol, &h->d_keys, &h->d_cntV, &h->d_cntT, &h->d_curT, &h->d_offV, &h->d_offT, &h->d_list,
+                    &h->d_rowbase, &h->d_perm, &h->d_misc, &h->d_vkeys, &h->d_faces, &h->d_verts, &h->d_normals})
+    b->release();
+  if (h->h_misc) cudaFreeHost(h->h_misc);
+  for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int zm_set_resolution(zm_handle* h, const float resolution[3]) {
+  if (!h || !resolution) return ZM_ERR_INVALID;
+  for (int i = 0; i < 3; ++i) h->res[i] = resolution[i];
+  h->fin = FinalState();
+  return ZM_OK;
+}
+
+int zm_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz,
+            int c_order, int close, int mem_kind) {
+  const uint64_t origin[3] = {0, 0, 0};
+  return run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, origin);
+}
+
+int zm_mesh_shard(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz,
+                  int c_order, int close, int mem_kind, const uint64_t origin[3]) {
+  if (!origin) return ZM_ERR_INVALID;
+  return run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, origin);
+}
+
+uint64_t zm_num_ids(zm_handle* h) { return h ? h->sorted_ids.size() : 0; }
+
+int zm_ids(zm_handle* h, uint64_t* out, uint64_t capacity) {
+  if (!h || (!out && capacity)) return ZM_ERR_INVALID;
+  uint64_t n = std::min<uint64_t>(capacity, h->sorted_ids.size());
+  if (n) memcpy(out, h->sorted_ids.data(), n * sizeof(uint64_t));
+  return ZM_OK;
+}
+
+int zm_get_counts(zm_handle* h, uint64_t label, uint64_t* nv, uint64_t* nf) {
+  if (!h || !nv || !nf) return ZM_ERR_INVALID;
+  *nv = *nf = 0;
+  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  auto it = h->index.find(label);
+  if (it == h->index.end() || h->recs[it->second].erased) return ZM_OK;
+  *nv = h->recs[it->second].nv;
+  *nf = h->recs[it->second].nt;
+  return ZM_OK;
+}
+
+int zm_get(zm_handle* h, uint64_t label, int normals, int voxel_centered, int transpose,
+           const float centering_offset[3], float* vertices, uint32_t* faces, float* normals_out) {
+  if (!h) return ZM_ERR_INVALID;
+  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  auto it = h->index.find(label);
+  if (it == h->index.end() || h->recs[it->second].erased) return ZM_OK;  // empty mesh
+  const LabelRec& r = h->recs[it->second];
+  if (!vertices || !faces || (normals && !normals_out)) return fail(h, ZM_ERR_INVALID, "null output buffer");
+  int rc = do_finalize(h, normals, voxel_centered, transpose, centering_offset);
+  if (rc != ZM_OK) return rc;
+  cudaStream_t st = h->stream;
+  ZM_CUDA(h, cudaMemcpyAsync(vertices, h->d_verts.as<float>() + 3 * r.voff, (size_t)r.nv * 12, cudaMemcpyDeviceToHost, st));
+  ZM_CUDA(h, cudaMemcpyAsync(faces, h->d_faces.as<uint32_t>() + 3 * r.foff, (size_t)r.nt * 12, cudaMemcpyDeviceToHost, st));
+  if (normals)
+    ZM_CUDA(h, cudaMemcpyAsync(normals_out, h->d_normals.as<float>() + 3 * r.voff, (size_t)r.nv * 12, cudaMemcpyDeviceToHost, st));
+  ZM_CUDA(h, cudaStreamSynchronize(st));
+  if (transpose) {  // legacy winding (t0,t2,t1) = stored (t1,t2,t0) reversed (cMesher.hpp:152-157)
+    for (uint64_t i = 0; i < r.nt; ++i) std::swap(faces[3 * i], faces[3 * i + 2]);
+  }
+  return ZM_OK;
+}
+
+int zm_erase(zm_handle* h, uint64_t label, int* existed) {
+  if (!h) return ZM_ERR_INVALID;
+  int ex = 0;
+  auto it = h->index.find(label);
+  if (it != h->index.end() && !h->recs[it->second].erased && h->recs[it->second].nt) {
+    h->recs[it->second].erased = true;
+    auto pos = std::lower_bound(h->sorted_ids.begin(), h->sorted_ids.end(), label);
+    if (pos != h->sorted_ids.end() && *pos == label) h->sorted_ids.erase(pos);
+    ex = 1;
+  }
+  if (existed) *existed = ex;
+  return ZM_OK;
+}
+
+int zm_clear(zm_handle* h) {
+  if (!h) return ZM_ERR_INVALID;
+  const bool had = h->has_result;
+  drop_results(h);
+  h->has_result = had;  // a cleared mesher answers like an empty one (marching_cubes.hpp:184-189)
+  cudaSetDevice(h->device);
+  for (DevBuf* b : {&h->d_vkeys, &h->d_faces, &h->d_verts, &h->d_normals, &h->d_perm, &h->d_vol}) b->release();
+  return ZM_OK;
+}
+
+int zm_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, const float centering_offset[3],
+                zm_bulk_view* view) {
+  if (!h) return ZM_ERR_INVALID;
+  int rc = do_finalize(h, normals, voxel_centered, transpose, centering_offset);
+  if (rc != ZM_OK) return rc;
+  if (view) {
+    if (h->bulk_labels.size() != h->recs.size() || h->bulk_voff.empty()) {
+      h->bulk_labels.clear(); h->bulk_voff.clear(); h->bulk_foff.clear();
+      for (const LabelRec& r : h->recs) {
+        h->bulk_labels.push_back(r.label);
+        h->bulk_voff.push_back(r.voff);
+        h->bulk_foff.push_back(r.foff);
+      }
+      h->bulk_voff.push_back(h->Vtot);
+      h->bulk_foff.push_back(h->Ttot);
+    }
+    view->n_labels = h->recs.size();
+    view->n_vertices = h->Vtot;
+    view->n_faces = h->Ttot;
+    view->labels_host = h->bulk_labels.data();
+    view->voff_host = h->bulk_voff.data();
+    view->foff_host = h->bulk_foff.data();
+    view->vertices_dev = h->Vtot ? h->d_verts.as<float>() : nullptr;
+    view->faces_dev = h->Ttot ? h->d_faces.as<uint32_t>() : nullptr;
+    view->normals_dev = (h->fin.normals && h->Vtot) ? h->d_normals.as<float>() : nullptr;
+  }
+  return ZM_OK;
+}
+
+int zm_fetch_all(zm_handle* h, float* vertices, uint32_t* faces, float* normals_out) {
+  if (!h) return ZM_ERR_INVALID;
+  if (!h->has_result || !h->fin.valid) return fail(h, ZM_ERR_STATE, "zm_finalize has not been called");
+  if (normals_out && !h->fin.normals) return fail(h, ZM_ERR_STATE, "normals were not requested in zm_finalize");
+  cudaStream_t st = h->stream;
+  if (h->Vtot && vertices)
+    ZM_CUDA(h, cudaMemcpyAsync(vertices, h->d_verts.p, (size_t)h->Vtot * 12, cudaMemcpyDeviceToHost, st));
+  if (h->Ttot && faces)
+    ZM_CUDA(h, cudaMemcpyAsync(faces, h->d_faces.p, (size_t)h->Ttot * 12, cudaMemcpyDeviceToHost, st));
+  if (h->Vtot && normals_out)
+    ZM_CUDA(h, cudaMemcpyAsync(normals_out, h->d_normals.p, (size_t)h->Vtot * 12, cudaMemcpyDeviceToHost, st));
+  ZM_CUDA(h, cudaStreamSynchronize(st));
+  if (h->fin.transpose && faces)
+    for (uint64_t i = 0; i < h->Ttot; ++i) std::swap(faces[3 * i], faces[3 * i + 2]);
+  return ZM_OK;
+}
+
+int zm_compute_normals(zm_handle* h, const float* vertices, uint64_t n_vertices, const uint32_t* faces,
+                       uint64_t n_faces, float* normals_out) {
+  if (!h) return ZM_ERR_INVALID;
+  if (n_vertices == 0) return ZM_OK;
+  if (!vertices || !normals_out || (n_faces && !faces)) return fail(h, ZM_ERR_INVALID, "null buffer");
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  DevBuf dv, df, dn;
+  auto cleanup = [&]() { dv.release(); df.release(); dn.release(); };
+  cudaError_t e;
+  if ((e = dv.ensure(n_vertices * 12)) != cudaSuccess || (e = df.ensure(n_faces * 12 + 16)) != cudaSuccess ||
+      (e = dn.ensure(n_vertices * 12)) != cudaSuccess) {
+    cleanup();
+    return fail(h, ZM_ERR_OOM, std::string("device allocation failed: ") + cudaGetErrorString(e));
+  }
+  int rc = ZM_OK;
+  do {
+    if ((e = cudaMemcpyAsync(dv.p, vertices, n_vertices * 12, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if (n_faces && (e = cudaMemcpyAsync(df.p, faces, n_faces * 12, cudaMemcpyHostToDevice, st)) != cudaSuccess) break;
+    if ((e = cudaMemsetAsync(dn.p, 0, n_vertices * 12, st)) != cudaSuccess) break;
+    if (n_faces) {
+      k_normals_accumulate_f32<<<grid_for(n_faces, 256), 256, 0, st>>>(dv.as<float>(), df.as<uint32_t>(), n_faces,
+                                                                       dn.as<float>());
+      if ((e = cudaGetLastError()) != cudaSuccess) break;
+    }
+    k_normals_normalize<<<grid_for(n_vertices, 256), 256, 0, st>>>(dn.as<float>(), n_vertices);
+    if ((e = cudaGetLastError()) != cudaSuccess) break;
+    if ((e = cudaMemcpyAsync(normals_out, dn.p, n_vertices * 12, cudaMemcpyDeviceToHost, st)) != cudaSuccess) break;
+    e = cudaStreamSynchronize(st);
+  } while (0);
+  if (e != cudaSuccess) rc = fail(h, ZM_ERR_CUDA, std::string("zm_compute_normals: ") + cudaGetErrorString(e));
+  cleanup();
+  return rc;
+}
+
+int zm_stats(zm_handle* h, zm_stats_t* out) {
+  if (!h || !out) return ZM_ERR_INVALID;
+  *out = h->stats;
+  return ZM_OK;
+}
+
+int zm_sync(zm_handle* h) {
+  if (!h) return ZM_ERR_INVALID;
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  ZM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return ZM_OK;
+}
+
+}  // extern "C"

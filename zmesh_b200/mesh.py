@@ -1,0 +1,143 @@
+"""`Mesh`: the value type returned by `Mesher.get` -- counterpart of the reference's
+zmesh/mesh.py:9-97 (container semantics) and :229-376 (Precomputed / OBJ / PLY codecs)."""
+from __future__ import annotations
+
+import re
+import struct
+from typing import Optional
+
+import numpy as np
+
+_PLY_HEADER = (
+  "ply\nformat binary_little_endian 1.0\nelement vertex {nv}\nproperty float x\nproperty float y\n"
+  "property float z\nelement face {nf}\nproperty list int int vertex_indices\nend_header\n"
+)
+
+
+class Mesh:
+  """vertices float32 (Nv,3); faces uint32 (Nf,3) (uint64 only beyond 2^32 vertices);
+  normals None or (Nv,3); id = label."""
+
+  def __init__(self, vertices=None, faces=None, normals=None, id: Optional[int] = None):
+    self.vertices = (np.zeros((0, 3), dtype=np.float32) if vertices is None
+                     else np.asarray(vertices, dtype=np.float32))
+    index_t = np.uint64 if self.vertices.shape[0] > np.iinfo(np.uint32).max else np.uint32
+    self.faces = np.zeros((0, 3), dtype=index_t) if faces is None else np.asarray(faces, dtype=index_t)
+    self.normals = None if normals is None else np.asarray(normals, dtype=np.float32)
+    self.id = id
+
+  # -- container protocol ---------------------------------------------------------------------
+  @property
+  def segid(self):
+    return self.id
+
+  @segid.setter
+  def segid(self, value):
+    self.id = value
+
+  def __len__(self) -> int:
+    return int(self.vertices.shape[0])
+
+  def _has_normals(self) -> bool:
+    return self.normals is not None and self.normals.size > 0
+
+  def __eq__(self, other) -> bool:
+    if self._has_normals() != other._has_normals():
+      return False
+    same = bool(np.all(self.vertices == other.vertices)) and bool(np.all(self.faces == other.faces))
+    if same and self._has_normals():
+      same = bool(np.all(self.normals == other.normals))
+    return same
+
+  def __ne__(self, other) -> bool:
+    return not self.__eq__(other)
+
+  __hash__ = None
+
+  def __repr__(self) -> str:
+    nn = None if self.normals is None else self.normals.shape[0]
+    return f"Mesh(vertices<{self.vertices.shape[0]}>, faces<{self.faces.shape[0]}>, normals<{nn}>)"
+
+  def empty(self) -> bool:
+    return self.faces.size == 0 or self.vertices.size == 0
+
+  @property
+  def nbytes(self) -> int:
+    return sum(a.nbytes for a in (self.vertices, self.faces, self.normals) if a is not None)
+
+  def clone(self) -> "Mesh":
+    n = None if self.normals is None else self.normals.copy()
+    return Mesh(self.vertices.copy(), self.faces.copy(), n, id=self.id)
+
+  def triangles(self) -> np.ndarray:
+    return self.vertices[self.faces]
+
+  @classmethod
+  def concatenate(cls, *meshes, id: Optional[int] = None) -> "Mesh":
+    starts = np.concatenate([[0], np.cumsum([len(m) for m in meshes])]).astype(np.uint64)
+    index_t = np.uint32 if starts[-1] < np.iinfo(np.uint32).max else np.uint64
+    verts = np.concatenate([m.vertices for m in meshes])
+    faces = np.concatenate([m.faces.astype(index_t, copy=False) + index_t(starts[i]) for i, m in enumerate(meshes)])
+    return cls(verts, faces, None, id=id)
+
+  # -- wire formats -----------------------------------------------------------------------------
+  def to_precomputed(self) -> bytes:
+    """Neuroglancer layout: uint32 Nv, Nv*3 float32, then uint32 face indices (no normals)."""
+    return b"".join((struct.pack("<I", self.vertices.shape[0]),
+                     np.ascontiguousarray(self.vertices, dtype="<f4").tobytes(),
+                     np.ascontiguousarray(self.faces).astype("<u4", copy=False).tobytes()))
+
+  @classmethod
+  def from_precomputed(cls, binary: bytes) -> "Mesh":
+    (nv,) = struct.unpack_from("<I", binary, 0)
+    need = 4 + 12 * nv
+    if len(binary) < need:
+      raise ValueError(f"Precomputed mesh buffer too small: need >= {need} bytes, got {len(binary)}")
+    verts = np.frombuffer(binary, dtype="<f4", count=3 * nv, offset=4).reshape(nv, 3)
+    faces = np.frombuffer(binary, dtype="<u4", offset=need)
+    return cls(verts, faces.reshape(-1, 3), None)
+
+  def to_ply(self) -> bytes:
+    out = bytearray(_PLY_HEADER.format(nv=self.vertices.shape[0], nf=self.faces.shape[0]).encode("utf8"))
+    out += np.ascontiguousarray(self.vertices, dtype="<f4").tobytes()
+    rec = np.empty((self.faces.shape[0], 4), dtype="<u4")
+    rec[:, 0] = 3
+    rec[:, 1:] = self.faces
+    out += rec.tobytes()
+    return out
+
+  @classmethod
+  def from_ply(cls, plydata: bytes) -> "Mesh":
+    """Reads the binary little-endian PLY dialect written by `to_ply` (and by the reference)."""
+    head, sep, body = bytes(plydata).partition(b"end_header\n")
+    if not sep or not head.startswith(b"ply"):
+      raise ValueError("not a binary PLY produced by to_ply")
+    counts = dict(re.findall(rb"element (vertex|face) (\d+)", head))
+    nv, nf = int(counts[b"vertex"]), int(counts[b"face"])
+    verts = np.frombuffer(body, dtype="<f4", count=3 * nv).reshape(nv, 3)
+    faces = np.frombuffer(body, dtype="<u4", count=4 * nf, offset=12 * nv).reshape(nf, 4)[:, 1:]
+    return cls(verts, faces, None)
+
+  def to_obj(self) -> bytes:
+    lines = ["v %.5f %.5f %.5f" % tuple(v) for v in self.vertices]
+    lines += ["f %d %d %d" % tuple(f) for f in (self.faces.astype(np.int64) + 1)]
+    return ("\n".join(lines) + "\n").encode("utf8")
+
+  @classmethod
+  def from_obj(cls, text) -> "Mesh":
+    if isinstance(text, bytes):
+      text = text.decode("utf8")
+    verts, faces, normals = [], [], []
+    for raw in text.splitlines():
+      tok = raw.split()
+      if not tok or tok[0].startswith("#"):
+        continue
+      if tok[0] == "v":
+        verts.append([float(t) for t in tok[1:4]])
+      elif tok[0] == "vn":
+        normals.append([float(t) for t in tok[1:4]])
+      elif tok[0] == "f":
+        faces.append([int(t.split("/")[0]) - 1 for t in tok[1:4]])
+    return cls(np.array(verts, dtype=np.float32).reshape(-1, 3),
+               np.array(faces, dtype=np.uint32).reshape(-1, 3),
+               np.array(normals, dtype=np.float32).reshape(-1, 3))

@@ -1,0 +1,241 @@
+"""`Mesher`: drop-in for the reference's Python class (zmesh/_zmesh.pyx:435-696) over the C ABI.
+
+Same methods, keyword names, defaults and observable quirks for the path
+`mesh(labels, close=) -> get(label, normals=, reduction_factor=0, voxel_centered=)`:
+
+  * labels of any 1/2/4/8-byte dtype are compared as unsigned bit patterns (:971, :1008);
+  * C- or Fortran-contiguous input is used in place, anything else is copied to C order (:499-500);
+  * close=True meshes the volume as if zero-padded by one voxel and does NOT shift the
+    coordinates back (:502-506);
+  * the resolution used for vertices is the one captured by mesh() (:494), the voxel_centered
+    offset uses the *current* `voxel_res` (:429-430, :581);
+  * normals come back as float64 (:151), missing labels give an empty Mesh with `.id` set;
+  * `ids()` is sorted ascending (the reference's order is unspecified).
+
+reduction_factor > 0 (mesh simplification) is outside this package's scope and raises
+NotImplementedError; there is no CPU fallback for anything.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .mesh import Mesh
+
+_ERR = {1: ValueError, 2: RuntimeError, 3: MemoryError, 4: ValueError, 5: RuntimeError}
+
+
+def _f3(a):
+  a = np.ascontiguousarray(a, dtype=np.float32)
+  if a.shape != (3,):
+    raise ValueError("voxel_res must have three components")
+  return a
+
+
+class Mesher:
+  """Represents a meshed volume: call mesher.mesh(labels), then mesher.get(label)."""
+
+  def __init__(self, voxel_res, device: int = -1):
+    self._lib = _lib.load()
+    self.voxel_res = voxel_res
+    self._device = int(device)
+    self._h = C.c_void_p()
+    self._max_label = None
+    res = self._voxel_res
+    rc = self._lib.zm_create(res.ctypes.data_as(C.POINTER(C.c_float)), self._device, C.byref(self._h))
+    if rc != 0:
+      msg = self._lib.zm_last_error(None)
+      raise _ERR.get(rc, RuntimeError)(f"zmesh_b200: {msg.decode() if msg else rc}")
+
+  def __del__(self):
+    h = getattr(self, "_h", None)
+    if h:
+      try:
+        self._lib.zm_destroy(h)
+      except Exception:
+        pass
+      self._h = None
+
+  # -- plumbing -----------------------------------------------------------------------------------
+  def _check(self, rc: int):
+    if rc != 0:
+      msg = self._lib.zm_last_error(self._h)
+      raise _ERR.get(rc, RuntimeError)(f"zmesh_b200: {msg.decode() if msg else rc}")
+
+  def _label_arg(self, label) -> int:
+    label = int(label)
+    if self._max_label is not None and not (0 <= label <= self._max_label):
+      # the reference's typed Cython signature raises the same for out-of-range ids
+      raise OverflowError("can't convert label to the meshed volume's label type")
+    if not (0 <= label < 2 ** 64):
+      raise OverflowError("label does not fit 64 bits")
+    return label
+
+  @property
+  def voxel_res(self):
+    return self._voxel_res
+
+  @voxel_res.setter
+  def voxel_res(self, res):
+    self._voxel_res = np.array(res, dtype=np.float32)
+
+  # -- the hot path -------------------------------------------------------------------------------
+  def mesh(self, data, close: bool = False, preserve_order: bool = True):
+    """Triggers the multi-label meshing process; afterwards call mesher.get.
+
+    data: 3d array (numpy, or any object exposing __cuda_array_interface__ such as a CUDA
+      torch tensor, which is consumed in place on the device).
+    close: close meshes that touch the volume boundary (virtual one-voxel zero border).
+    preserve_order: accepted for compatibility, ignored (as in the reference)."""
+    res = _f3(self._voxel_res)
+    self._check(self._lib.zm_set_resolution(self._h, res.ctypes.data_as(C.POINTER(C.c_float))))
+
+    cai = getattr(data, "__cuda_array_interface__", None)
+    if cai is not None and not isinstance(data, np.ndarray):
+      return self._mesh_device(data, cai, bool(close))
+
+    data = np.asarray(data) if not isinstance(data, np.ndarray) else data
+    if data.ndim < 3:
+      raise IndexError("tuple index out of range")  # the reference indexes data.shape[2]
+    nbytes = data.dtype.itemsize
+    if nbytes not in (1, 2, 4, 8):
+      raise TypeError(f"unsupported label dtype {data.dtype}")
+    shape = tuple(int(s) for s in data.shape[:3])
+    if int(np.prod(data.shape, dtype=np.int64)) != shape[0] * shape[1] * shape[2]:
+      raise ValueError("only the first three axes may have extent > 1")
+    if data.ndim > 3:
+      data = data.reshape(shape, order="C" if data.flags.c_contiguous else "F") \
+        if (data.flags.c_contiguous or data.flags.f_contiguous) else data.reshape(shape)
+    if not data.flags.c_contiguous and not data.flags.f_contiguous:
+      data = np.ascontiguousarray(data)
+    c_order = 1 if data.flags.c_contiguous else 0
+    self._max_label = (1 << (8 * nbytes)) - 1
+    self._check(self._lib.zm_mesh(self._h, C.c_void_p(data.ctypes.data), nbytes, shape[0], shape[1], shape[2],
+                                  c_order, 1 if close else 0, 0))
+
+  def _mesh_device(self, obj, cai, close: bool):
+    shape = tuple(int(s) for s in cai["shape"])
+    if len(shape) < 3:
+      raise IndexError("tuple index out of range")
+    if len(shape) > 3:
+      if int(np.prod(shape[3:])) != 1:
+        raise ValueError("only the first three axes may have extent > 1")
+    typestr = cai["typestr"]
+    nbytes = int(typestr[2:])
+    if nbytes not in (1, 2, 4, 8):
+      raise TypeError(f"unsupported label dtype {typestr}")
+    strides = cai.get("strides")
+    s3 = shape[:3]
+    c_strides = (s3[1] * s3[2] * nbytes, s3[2] * nbytes, nbytes)
+    f_strides = (nbytes, s3[0] * nbytes, s3[0] * s3[1] * nbytes)
+    if strides is None or tuple(strides[:3]) == c_strides:
+      c_order = 1
+    elif tuple(strides[:3]) == f_strides:
+      c_order = 0
+    else:
+      raise ValueError("device arrays must be C- or Fortran-contiguous")
+    ptr = int(cai["data"][0])
+    self._max_label = (1 << (8 * nbytes)) - 1
+    self._check(self._lib.zm_mesh(self._h, C.c_void_p(ptr), nbytes, s3[0], s3[1], s3[2], c_order,
+                                  1 if close else 0, 1))
+
+  def ids(self):
+    n = int(self._lib.zm_num_ids(self._h))
+    out = np.empty(n, dtype=np.uint64)
+    if n:
+      self._check(self._lib.zm_ids(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64)), n))
+    return out.tolist()
+
+  def _fetch(self, label, normals: bool, voxel_centered: bool, transpose: bool) -> Mesh:
+    label = self._label_arg(label)
+    nv, nf = C.c_uint64(0), C.c_uint64(0)
+    self._check(self._lib.zm_get_counts(self._h, label, C.byref(nv), C.byref(nf)))
+    if nv.value == 0 or nf.value == 0:
+      mesh = Mesh()
+      mesh.id = label
+      return mesh
+    verts = np.empty((nv.value, 3), dtype=np.float32)
+    faces = np.empty((nf.value, 3), dtype=np.uint32)
+    nrm = np.empty((nv.value, 3), dtype=np.float32) if normals else None
+    off = _f3(self._voxel_res)
+    self._check(self._lib.zm_get(
+      self._h, label, 1 if normals else 0, 1 if voxel_centered else 0, 1 if transpose else 0,
+      off.ctypes.data_as(C.POINTER(C.c_float)), C.c_void_p(verts.ctypes.data), C.c_void_p(faces.ctypes.data),
+      C.c_void_p(nrm.ctypes.data) if normals else None))
+    mesh = Mesh(verts, faces, None)
+    if normals:
+      mesh.normals = nrm.astype(np.float64)  # the reference hands back float64 (zmesh/_zmesh.pyx:151)
+    mesh.id = label
+    return mesh
+
+  def get(self, label, normals=False, reduction_factor=0, max_error=None, voxel_centered=False) -> Mesh:
+    """label: the integer id of the mesh
+    normals: whether to calculate vertex normals
+    reduction_factor: must be 0 (simplification is out of scope of this package)
+    voxel_centered: centre the mesh in the voxel (0.5, 0.5, 0.5) instead of at (0, 0, 0)."""
+    if reduction_factor:
+      raise NotImplementedError("zmesh_b200 covers reduction_factor=0 only (no mesh simplification)")
+    return self._fetch(label, bool(normals), bool(voxel_centered), transpose=False)
+
+  def get_mesh(self, mesh_id, normals=False, simplification_factor=0, max_simplification_error=40,
+               voxel_centered=False) -> Mesh:
+    """Deprecated accessor kept for compatibility: like get() but with x and z swapped."""
+    if simplification_factor:
+      raise NotImplementedError("zmesh_b200 covers simplification_factor=0 only")
+    return self._fetch(mesh_id, bool(normals), bool(voxel_centered), transpose=True)
+
+  def compute_normals(self, mesh: Mesh) -> Mesh:
+    verts = np.ascontiguousarray(mesh.vertices, dtype=np.float32)
+    faces = np.ascontiguousarray(mesh.faces, dtype=np.uint32)
+    out = np.zeros((verts.shape[0], 3), dtype=np.float32)
+    self._check(self._lib.zm_compute_normals(self._h, C.c_void_p(verts.ctypes.data), verts.shape[0],
+                                             C.c_void_p(faces.ctypes.data), faces.shape[0],
+                                             C.c_void_p(out.ctypes.data)))
+    mesh.normals = out.astype(np.float64)
+    return mesh
+
+  def simplify(self, *args, **kwargs):
+    raise NotImplementedError("zmesh_b200 covers reduction_factor=0 only (no mesh simplification)")
+
+  def erase(self, segid) -> bool:
+    existed = C.c_int(0)
+    self._check(self._lib.zm_erase(self._h, self._label_arg(segid), C.byref(existed)))
+    return bool(existed.value)
+
+  def clear(self):
+    self._check(self._lib.zm_clear(self._h))
+
+  # -- extras (no reference counterpart) ------------------------------------------------------------
+  def stats(self) -> dict:
+    st = _lib.zm_stats_t()
+    self._check(self._lib.zm_stats(self._h, C.byref(st)))
+    return {name: getattr(st, name) for name, _ in st._fields_}
+
+  def finalize(self, normals=False, voxel_centered=False, transpose=False):
+    """Run the final gather for all labels on the device; returns the bulk directory."""
+    view = _lib.zm_bulk_view()
+    off = _f3(self._voxel_res)
+    self._check(self._lib.zm_finalize(self._h, int(bool(normals)), int(bool(voxel_centered)), int(bool(transpose)),
+                                      off.ctypes.data_as(C.POINTER(C.c_float)), C.byref(view)))
+    n = int(view.n_labels)
+    as_np = lambda p, k: (np.ctypeslib.as_array(p, shape=(k,)).copy() if k else np.zeros(0, dtype=np.uint64))
+    return {
+      "labels": as_np(view.labels_host, n), "voff": as_np(view.voff_host, n + 1), "foff": as_np(view.foff_host, n + 1),
+      "n_vertices": int(view.n_vertices), "n_faces": int(view.n_faces),
+      "vertices_dev": view.vertices_dev, "faces_dev": view.faces_dev, "normals_dev": view.normals_dev,
+    }
+
+  def fetch_all(self, normals=False):
+    """After finalize(): all labels' arrays in one device-to-host transfer each."""
+    st = self.stats()
+    v = np.empty((st["n_vertices"], 3), dtype=np.float32)
+    f = np.empty((st["n_faces"], 3), dtype=np.uint32)
+    n = np.empty((st["n_vertices"], 3), dtype=np.float32) if normals else None
+    self._check(self._lib.zm_fetch_all(self._h, C.c_void_p(v.ctypes.data), C.c_void_p(f.ctypes.data),
+                                       C.c_void_p(n.ctypes.data) if normals else None))
+    return v, f, n
+
+  def sync(self):
+    self._check(self._lib.zm_sync(self._h))
