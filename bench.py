@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path: Mesher.mesh(labels) + Mesher.get(id, rf=0) for
+ALL labels, in megavoxels per second (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5] [--impl ours|reference]
+
+One process per GPU (torchrun for N > 1).  A "step" is one pass of the whole pipeline over the
+workload volume: classify -> label scan -> emit -> final gather (-> normals).  Reported:
+
+  value      device-resident throughput: labels already in HBM -> final per-label vertex / face
+             (/ normal) arrays in HBM; CUDA events on the launching stream, max over ranks
+  e2e        the same metric through the drop-in Python API with HOST buffers: mesher.mesh(numpy)
+             + mesher.get(i) for every id (H2D of the volume and D2H of every mesh inside the
+             timed region)
+  roofline   dominant kernel: algorithmic bytes per launch / its measured duration vs HBM peak
+  cpu_baseline  the reference's CPU implementation timed on this box's host cores on a bounded
+             sample of the same workload (rank 0, N = 1)
+
+Workloads (BASELINE.json `configs`): c1 connectomics.npy 512^3 u32; c2a zeros / c2b ones(close)
+512^3 u32; c3 random [0,1000) 512^3 u32; c4 Voronoi 1024^3 u64 close+normals+voxel_centered;
+c5 Voronoi 2048^3 u64 (default: the config the multi-GPU metric is quoted on; z-slab sharded
+across ranks, strong scaling).
+"""
+import argparse
+import gzip
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+  # name: (kind, shape, dtype, order, res, close, normals, voxel_centered, extra)
+  "c1": dict(kind="connectomics", shape=(512, 512, 512), dtype="uint32", order="F", res=(4, 4, 40), close=False, normals=False, vc=False),
+  "c2a": dict(kind="zeros", shape=(512, 512, 512), dtype="uint32", order="C", res=(4, 4, 40), close=False, normals=False, vc=False),
+  "c2b": dict(kind="ones", shape=(512, 512, 512), dtype="uint32", order="C", res=(4, 4, 40), close=True, normals=False, vc=False),
+  "c3": dict(kind="random", shape=(512, 512, 512), dtype="uint32", order="C", res=(4, 4, 40), close=False, normals=False, vc=False),
+  "c4": dict(kind="voronoi", shape=(1024, 1024, 1024), dtype="uint64", order="F", res=(4, 4, 40), close=True, normals=True, vc=True, pitch=64),
+  "c5": dict(kind="voronoi", shape=(2048, 2048, 2048), dtype="uint64", order="F", res=(4, 4, 40), close=False, normals=False, vc=False, pitch=128),
+  # reduced-size stand-ins for development (never the default)
+  "c5s": dict(kind="voronoi", shape=(512, 512, 512), dtype="uint64", order="F", res=(4, 4, 40), close=False, normals=False, vc=False, pitch=128),
+}
+
+
+def describe(name, wl, extra=None):
+  d = {"workload": f"{name}: {wl['kind']} {'x'.join(map(str, wl['shape']))} {wl['dtype']} {wl['order']}-order"
+                   + (f" pitch {wl['pitch']}" if 'pitch' in wl else ""),
+       "resolution": list(wl["res"]), "close": wl["close"], "normals": wl["normals"],
+       "voxel_centered": wl["vc"], "reduction_factor": 0}
+  d.update(extra or {})
+  return d
+
+
+def load_peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    try:
+      return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+      pass
+  return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons DURING the timed region."""
+  Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index=0):
+    self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+
+  def _run(self):
+    while not self.stop.is_set():
+      try:
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+          self.rows.append([c.strip() for c in out.splitlines()[0].split(",")])
+      except Exception:
+        pass
+      self.stop.wait(0.2)
+
+  def __enter__(self):
+    self.t = threading.Thread(target=self._run, daemon=True)
+    self.t.start()
+    return self
+
+  def __exit__(self, *a):
+    self.stop.set()
+    self.t.join(timeout=6)
+
+  def summary(self):
+    sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+    mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload construction
+
+def host_volume(name, wl, zrange=None):
+  """Host numpy array of the workload (or of z-planes [z0, z1) of it)."""
+  shape, dt = wl["shape"], np.dtype(wl["dtype"])
+  if wl["kind"] == "connectomics":
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "connectomics.npy.gz"), "rb") as f:
+      v = np.load(f)
+  elif wl["kind"] == "zeros":
+    v = np.zeros(shape, dtype=dt)
+  elif wl["kind"] == "ones":
+    v = np.ones(shape, dtype=dt)
+  elif wl["kind"] == "random":
+    v = np.random.default_rng(0).integers(0, 1000, size=shape, dtype=dt)
+  else:
+    raise ValueError("voronoi volumes are generated on the device")
+  if zrange is not None:
+    v = np.asarray(v[:, :, zrange[0]:zrange[1]], order=wl["order"])
+  return v
+
+
+def device_volume(name, wl, device, zrange=None):
+  """torch CUDA tensor holding the workload (z-planes [z0,z1) of it when sharded)."""
+  import torch
+  from zmesh_b200.synth import voronoi_device
+  shape = wl["shape"]
+  z0, z1 = zrange if zrange is not None else (0, shape[2])
+  if wl["kind"] == "voronoi":
+    return voronoi_device((shape[0], shape[1], z1 - z0), wl["pitch"], np.dtype(wl["dtype"]), seed=0, order=wl["order"],
+                          origin=(0, 0, z0), full_shape=shape, device=device)
+  v = host_volume(name, wl, zrange if zrange is not None else None)
+  nb = v.dtype.itemsize
+  sdt = {1: np.uint8, 2: np.int16, 4: np.int32, 8: np.int64}[nb]
+  if v.flags.c_contiguous:
+    return torch.from_numpy(v.view(sdt)).to(f"cuda:{device}")
+  t = torch.from_numpy(np.ascontiguousarray(v.transpose(2, 1, 0)).view(sdt)).to(f"cuda:{device}")
+  return t.permute(2, 1, 0)
+
+
+def slab_range(shape_z, rank, world):
+  """Cube-origin planes [a_r, a_{r+1}) of rank r -> voxel planes [a_r, a_{r+1}] (1-plane halo)."""
+  ncube = shape_z - 1
+  a0 = (ncube * rank) // world
+  a1 = (ncube * (rank + 1)) // world
+  return a0, a1 + 1
+
+
+# ------------------------------------------------------------------------------------------------
+
+def run_reference(args, name, wl):
+  """--impl reference: the reference's own CPU implementation (oracle/_ref when it was compiled
+  from /root/reference, else the C port) timed on this box's host cores on a bounded sample."""
+  from oracle import oracle as O
+  O.build()
+  kind = "reference" if O.have_reference() else "port"
+  sample, sample_desc = cpu_sample(name, wl)
+  res, close, normals, vc = wl["res"], wl["close"], wl["normals"], wl["vc"]
+
+  def step():
+    m = O.OracleMesher(res, kind)
+    m.mesh(sample, close=close)
+    for i in m.ids():
+      m.get(i, normals=normals, voxel_centered=vc)
+
+  for _ in range(args.warmup):
+    step()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    step()
+  dt = (time.perf_counter() - t0) / args.steps
+  mvx = sample.size / 1e6 / dt
+  line = {
+    "impl": "reference", "metric": "MVx/s mesh+get(rf=0)", "value": mvx, "unit": "MVx/s", "n_gpus": args.gpus,
+    "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+    "scaling": "strong", "vs_baseline": None, "dtype": "u" + str(8 * np.dtype(wl["dtype"]).itemsize),
+    "data": "synthetic" if wl["kind"] != "connectomics" else "connectomics.npy (reference sample volume)",
+    "config": describe(name, wl, {"sample": sample_desc}),
+    "cpu_baseline": {"value": mvx, "unit": "MVx/s", "cores": 1, "kind": kind, "sample": sample_desc,
+                     "note": "the reference is single-threaded (no threads/SIMD/GIL release); 1 core is all it can use"},
+    "e2e": {"value": mvx, "unit": "MVx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def cpu_sample(name, wl):
+  """Bounded sample of the workload for the CPU arm (about 5-15 s of single-core work)."""
+  shape = wl["shape"]
+  if wl["kind"] == "voronoi":
+    nz = max(8, min(shape[2], int(48e6 // (shape[0] * shape[1]))))
+    try:
+      import torch
+      if torch.cuda.is_available():
+        t = device_volume(name, wl, 0, (0, nz))
+        torch.cuda.synchronize()
+        v = t.cpu().numpy().view(np.dtype(wl["dtype"]))
+        del t
+        return v, f"z-planes [0,{nz}) of the workload volume ({shape[0]}x{shape[1]}x{nz})"
+    except Exception:
+      pass
+    from oracle.oracle import voronoi_volume
+    side = 256
+    v = voronoi_volume((side, side, 64), wl["pitch"], np.dtype(wl["dtype"]), 0, wl["order"], full_shape=shape)
+    return v, f"corner block {side}x{side}x64 of the workload volume (numpy generator, no GPU)"
+  if wl["kind"] == "random":
+    v = host_volume(name, wl, (0, 24))
+    return v, f"z-planes [0,24) of the workload volume ({shape[0]}x{shape[1]}x24)"
+  if wl["kind"] == "connectomics":
+    v = host_volume(name, wl, (0, 160))
+    return v, "z-planes [0,160) of connectomics.npy (512x512x160)"
+  v = host_volume(name, wl)
+  return v, "full volume"
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=5)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--workload", default=os.environ.get("ZM_BENCH_WORKLOAD", "c5"), choices=sorted(WORKLOADS))
+  ap.add_argument("--e2e-steps", type=int, default=2)
+  ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--no-cpu", action="store_true")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+  name, wl = args.workload, WORKLOADS[args.workload]
+
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+  if args.impl == "reference":
+    if rank == 0:
+      run_reference(args, name, wl)
+    return
+
+  import torch
+  import torch.distributed as dist
+  import __graft_entry__ as G
+  if rank == 0:
+    G.build()
+  if world > 1:
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    dist.barrier()
+  from zmesh_b200 import Mesher
+
+  dev = local_rank
+  torch.cuda.set_device(dev)
+  shape = wl["shape"]
+  nvox_total = int(np.prod(shape))
+  label_bytes = np.dtype(wl["dtype"]).itemsize
+  zr = slab_range(shape[2], rank, world) if world > 1 else (0, shape[2])
+  origin = (0, 0, zr[0])
+  vol = device_volume(name, wl, dev, zr if world > 1 else None)
+  torch.cuda.synchronize()
+
+  mesher = Mesher(wl["res"], device=dev)
+  stream = torch.cuda.current_stream()
+  mesher.set_stream(stream.cuda_stream)
+
+  def step():
+    if world > 1:
+      mesher.mesh_shard(vol, origin, close=wl["close"])
+    else:
+      mesher.mesh(vol, close=wl["close"])
+    mesher.finalize(normals=wl["normals"], voxel_centered=wl["vc"])
+    return mesher.stats()
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  for _ in range(args.warmup):
+    st = step()
+  barrier()
+  acc = {k: 0.0 for k in ("ms_classify", "ms_scan", "ms_emit", "ms_finalize", "ms_total")}
+  launches = 0
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  with ClockSampler(dev) as clocks:
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+      st = step()
+      for k in acc:
+        acc[k] += st[k]
+      launches += st["launches"] + st["launches_finalize"]
+    ev1.record(stream)
+    barrier()
+  ms = ev0.elapsed_time(ev1) / args.steps
+  if world > 1:
+    t = torch.tensor([ms], device=f"cuda:{dev}", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    cnt = torch.tensor([st["n_vertices"], st["n_faces"], st["n_labels"]], device=f"cuda:{dev}", dtype=torch.int64)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    totV, totT = int(cnt[0]), int(cnt[1])
+  else:
+    totV, totT = st["n_vertices"], st["n_faces"]
+  value = nvox_total / 1e6 / (ms / 1e3)
+
+  # ---- roofline of the dominant kernel (rank-local averages) -----------------------------------
+  peak, peak_src = load_peaks()
+  nvox_local = int(np.prod(vol.shape))
+  V, T = st["n_vertices"], st["n_faces"]
+  kern = {
+    "k_classify": (acc["ms_classify"] / args.steps, nvox_local * label_bytes + 4 * V),
+    "k_emit": (acc["ms_emit"] / args.steps, nvox_local * label_bytes + 8 * V + 12 * T + 4 * V),
+    "k_finalize": (acc["ms_finalize"] / args.steps, 8 * V + 12 * V + (12 * T + 12 * V if wl["normals"] else 0)),
+  }
+  dom = max(kern, key=lambda k: kern[k][0])
+  dom_ms, dom_bytes = kern[dom]
+  achieved = dom_bytes / 1e9 / (dom_ms / 1e3) if dom_ms > 0 else 0.0
+  traffic = None
+  tp = os.path.join(ROOT, "profiles", "traffic.json")
+  if os.path.exists(tp):
+    try:
+      traffic = json.load(open(tp)).get(name, {}).get(dom)
+    except Exception:
+      traffic = None
+  b_alg = nvox_local * label_bytes + 12 * V + 12 * T + (12 * V if wl["normals"] else 0)
+  roofline = {
+    "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
+    "kernel_ms": {k: v[0] for k, v in kern.items()},
+    "pipeline": {"algorithmic_bytes": b_alg, "ms": ms, "achieved": b_alg / 1e9 / (ms / 1e3),
+                 "frac": b_alg / 1e9 / (ms / 1e3) / peak,
+                 "note": "SURVEY 8d: N*sizeof(label) + 12 B/vertex + 12 B/triangle (+12 B/vertex normals), rank-local"},
+  }
+
+  # ---- end to end through the drop-in API with host buffers ------------------------------------
+  e2e = None
+  if not args.no_e2e:
+    mesher.set_stream(None)
+    host = vol.cpu()  # rank-local slab, host memory
+    hnp = host.numpy() if not isinstance(host, np.ndarray) else host
+    hnp = hnp.view(np.dtype(wl["dtype"]))
+    del vol
+    torch.cuda.empty_cache()
+    try:
+      pinned = torch.cuda.cudart().cudaHostRegister(hnp.ctypes.data, hnp.nbytes, 0)
+    except Exception:
+      pinned = None
+    d2h = 0
+
+    def e2e_step():
+      nonlocal d2h
+      if world > 1:
+        mesher.mesh_shard(hnp, origin, close=wl["close"])
+      else:
+        mesher.mesh(hnp, close=wl["close"])
+      d2h = 0
+      for i in mesher.ids():
+        m = mesher.get(i, normals=wl["normals"], reduction_factor=0, voxel_centered=wl["vc"])
+        d2h += m.vertices.nbytes + m.faces.nbytes + (m.vertices.nbytes if wl["normals"] else 0)
+
+    e2e_step()  # warm-up (allocations, page faults)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+      e2e_step()
+    barrier()
+    dt = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+      t = torch.tensor([dt], device=f"cuda:{dev}", dtype=torch.float64)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      dt = float(t.item())
+    e2e = {"value": nvox_total / 1e6 / dt, "unit": "MVx/s", "h2d_bytes_per_step": int(hnp.nbytes),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+           "host_buffer": "cudaHostRegister'ed numpy" if pinned is not None else "pageable numpy",
+           "api": "zmesh_b200.Mesher.mesh(ndarray) + get(id) for every id (rank-local slab when sharded)"}
+
+  # ---- CPU baseline beside it (rank 0, N = 1) ---------------------------------------------------
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu:
+    from oracle import oracle as O
+    kind = "reference" if O.have_reference() else "port"
+    sample, sdesc = cpu_sample(name, wl)
+    t0 = time.perf_counter()
+    m = O.OracleMesher(wl["res"], kind)
+    m.mesh(sample, close=wl["close"])
+    for i in m.ids():
+      m.get(i, normals=wl["normals"], voxel_centered=wl["vc"])
+    dt = time.perf_counter() - t0
+    cpu = {"value": sample.size / 1e6 / dt, "unit": "MVx/s", "cores": 1, "kind": kind, "sample": sdesc,
+           "seconds": dt, "host_cpus": os.cpu_count()}
+
+  if rank == 0:
+    line = {
+      "metric": "MVx/s mesh+get(rf=0)", "value": value, "unit": "MVx/s", "n_gpus": world, "steps": args.steps,
+      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+      "dtype": "u" + str(8 * label_bytes),
+      "data": "synthetic" if wl["kind"] != "connectomics" else "connectomics.npy (reference sample volume)",
+      "config": describe(name, wl, {
+        "l2": "inputs larger than L2 (volume %.1f GB per rank >> 126 MB)" % (nvox_local * label_bytes / 1e9),
+        "sharding": (f"z-slabs with 1-plane halo over {world} ranks, global keys; per-shard partial meshes "
+                     "(cross-shard weld of shared-plane vertices not included)") if world > 1 else "single GPU",
+        "labels": int(st["n_labels"]), "vertices": int(totV), "faces": int(totT)}),
+      "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+      "clocks": clocks.summary(),
+    }
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -43,6 +43,10 @@ enum { ZM_MEM_HOST = 0, ZM_MEM_DEVICE = 1 };
 int zm_create(const float resolution[3], int device, zm_handle** out);
 void zm_destroy(zm_handle* h);
 
+/* Run all work of this handle on a caller-owned CUDA stream (cudaStream_t passed as void*, e.g.
+ * torch.cuda.current_stream().cuda_stream) instead of the handle's own; NULL restores the own one. */
+int zm_set_stream(zm_handle* h, void* cuda_stream);
+
 /* Replaces the resolution captured by `MesherClass(self.voxel_res)` in Mesher.mesh
  * (zmesh/_zmesh.pyx:494): call before zm_mesh to re-capture. */
 int zm_set_resolution(zm_handle* h, const float resolution[3]);
@@ -135,6 +139,15 @@ typedef struct {
   uint32_t launches_finalize;
 } zm_stats_t;
 int zm_stats(zm_handle* h, zm_stats_t* out);
+
+/* Synthetic input for benchmarks/tests: integer jittered-grid Voronoi segmentation (SURVEY.md
+ * section 8d) written straight into device memory.  Generates the sub-block `shape` at `origin`
+ * of a volume of `full_shape`; one site per cell of side `pitch`; nearest site among the 27
+ * neighbouring cells wins, ties to the smaller cell id; label = splitmix64(cell+1)|1 for 8-byte
+ * labels, cell+1 otherwise.  Bit-identical to oracle/oracle.py:voronoi_volume. */
+int zm_synth_voronoi(void* dst_device, int label_bytes, const uint64_t shape[3], const uint64_t origin[3],
+                     const uint64_t full_shape[3], uint32_t pitch, uint64_t seed, int c_order,
+                     void* cuda_stream);
 
 /* Blocks until all work queued by this handle has finished. */
 int zm_sync(zm_handle* h);

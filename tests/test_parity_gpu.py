@@ -215,7 +215,8 @@ def test_degenerate_volumes_512(Mesher):
   uniq, cnt = np.unique(ek, return_counts=True)
   assert (cnt == 2).all()
   assert len(g.vertices) - len(uniq) + len(g.faces) == 2
-  assert g.vertices.min() == 2.0 and g.vertices[:, 2].max() == 513.0 * 20
+  # padded coordinates: the surface lies at keys 1 and 2*512+1 (half-voxel units)
+  assert g.vertices.min() == 2.0 and g.vertices[:, 2].max() == 1025.0 * 20
 
 
 def test_connectomics_full_against_reference_digests(Mesher, connectomics):
@@ -286,3 +287,27 @@ def test_vertex_census_identity_random256(Mesher):
     ff = f[bulk["foff"][i]:bulk["foff"][i + 1]]
     nv = int(bulk["voff"][i + 1] - bulk["voff"][i])
     assert ff.max() < nv and len(np.unique(ff)) == nv
+
+
+@pytest.mark.parametrize("order", ["C", "F"])
+@pytest.mark.parametrize("dtype", [np.uint64, np.uint32])
+def test_device_generator_matches_numpy(Mesher, order, dtype):
+  """zm_synth_voronoi (bench input) is bit-identical to the numpy generator, incl. sub-blocks."""
+  import torch
+  from zmesh_b200.synth import voronoi_device
+  full = (70, 60, 50)
+  origin, shape = (10, 0, 7), (45, 60, 30)
+  want = voronoi_volume(shape, 16, dtype, seed=3, order=order, origin=origin, full_shape=full)
+  t = voronoi_device(shape, 16, dtype, seed=3, order=order, origin=origin, full_shape=full)
+  torch.cuda.synchronize()
+  got = t.cpu().numpy().view(dtype)
+  assert got.shape == want.shape and np.array_equal(got, want)
+  gpu, cpu = Mesher((4, 4, 40)), OracleMesher((4, 4, 40), "port")
+  gpu.mesh_shard(t, origin)
+  cpu.mesh(want)
+  assert gpu.ids() == sorted(cpu.ids())
+  shift = np.array(origin, dtype=np.float32) * np.array([4, 4, 40], dtype=np.float32)
+  for lbl in gpu.ids()[:20]:
+    w = cpu.get(lbl)
+    w.vertices += shift
+    assert_same_mesh(gpu.get(lbl), w, what=str(lbl))

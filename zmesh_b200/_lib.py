@@ -58,6 +58,8 @@ SYMBOLS = {
   "zm_create": (C.c_int, [_f3, C.c_int, C.POINTER(C.c_void_p)]),
   "zm_destroy": (None, [C.c_void_p]),
   "zm_set_resolution": (C.c_int, [C.c_void_p, _f3]),
+  "zm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+  "zm_synth_voronoi": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]),
   "zm_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]),
   "zm_mesh_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, _u64p]),
   "zm_num_ids": (C.c_uint64, [C.c_void_p]),

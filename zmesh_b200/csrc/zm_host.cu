@@ -55,7 +55,8 @@ struct FinalState {
 
 struct zm_handle {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // the stream all work is queued on
+  cudaStream_t own_stream = nullptr;  // created by zm_create (stream == own_stream unless zm_set_stream)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float res[3] = {1, 1, 1};
   std::string err;
@@ -422,7 +423,8 @@ int zm_create(const float resolution[3], int device, zm_handle** out) {
     return ZM_ERR_CUDA;
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
-  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  h->stream = h->own_stream;
   for (auto& ev : h->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaHostAlloc((void**)&h->h_misc, 64, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
@@ -446,8 +448,40 @@ void zm_destroy(zm_handle* h) {
   if (h->h_misc) cudaFreeHost(h->h_misc);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
+}
+
+int zm_set_stream(zm_handle* h, void* cuda_stream) {
+  if (!h) return ZM_ERR_INVALID;
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  ZM_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+  return ZM_OK;
+}
+
+int zm_synth_voronoi(void* dst, int label_bytes, const uint64_t shape[3], const uint64_t origin[3],
+                     const uint64_t full_shape[3], uint32_t pitch, uint64_t seed, int c_order, void* cuda_stream) {
+  if (!dst || !shape || !origin || !full_shape || pitch == 0) return ZM_ERR_INVALID;
+  if (label_bytes != 1 && label_bytes != 2 && label_bytes != 4 && label_bytes != 8) return ZM_ERR_INVALID;
+  SynthArgs a{};
+  a.dst = dst;
+  a.sx = (uint32_t)shape[0]; a.sy = (uint32_t)shape[1]; a.sz = (uint32_t)shape[2];
+  a.n = (unsigned long long)shape[0] * shape[1] * shape[2];
+  a.ox = (uint32_t)origin[0]; a.oy = (uint32_t)origin[1]; a.oz = (uint32_t)origin[2];
+  auto cells = [&](uint64_t s) { uint64_t g = (s + pitch - 1) / pitch; return (uint32_t)(g ? g : 1); };
+  a.gx = cells(full_shape[0]); a.gy = cells(full_shape[1]); a.gz = cells(full_shape[2]);
+  a.pitch = pitch; a.seed = seed; a.c_order = c_order;
+  if (a.n == 0) return ZM_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const uint32_t grid = grid_for(a.n, 256) * 4;
+  switch (label_bytes) {
+    case 1: k_synth_voronoi<uint8_t><<<grid, 256, 0, st>>>(a); break;
+    case 2: k_synth_voronoi<uint16_t><<<grid, 256, 0, st>>>(a); break;
+    case 4: k_synth_voronoi<uint32_t><<<grid, 256, 0, st>>>(a); break;
+    default: k_synth_voronoi<unsigned long long><<<grid, 256, 0, st>>>(a); break;
+  }
+  return cudaGetLastError() == cudaSuccess ? ZM_OK : ZM_ERR_CUDA;
 }
 
 int zm_set_resolution(zm_handle* h, const float resolution[3]) {

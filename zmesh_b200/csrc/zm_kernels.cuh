@@ -841,4 +841,56 @@ __global__ void __launch_bounds__(256) k_normals_normalize(float* normals, unsig
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// synthetic jittered-grid Voronoi volume (benchmark/test input)
+
+__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  unsigned long long z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+struct SynthArgs {
+  void* dst;
+  unsigned long long n;  // voxels of the block
+  uint32_t sx, sy, sz;   // block shape (logical)
+  uint32_t ox, oy, oz;   // block origin inside the full volume
+  uint32_t gx, gy, gz;   // cells per axis of the full volume
+  uint32_t pitch;
+  unsigned long long seed;
+  int c_order;
+};
+
+template <typename L>
+__global__ void __launch_bounds__(256) k_synth_voronoi(const SynthArgs a) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (; i < a.n; i += stride) {
+    uint32_t lx, ly, lz;
+    if (a.c_order) { lz = (uint32_t)(i % a.sz); unsigned long long t = i / a.sz; ly = (uint32_t)(t % a.sy); lx = (uint32_t)(t / a.sy); }
+    else           { lx = (uint32_t)(i % a.sx); unsigned long long t = i / a.sx; ly = (uint32_t)(t % a.sy); lz = (uint32_t)(t / a.sy); }
+    const long long x = (long long)lx + a.ox, y = (long long)ly + a.oy, z = (long long)lz + a.oz;
+    const int bi = (int)(x / a.pitch), bj = (int)(y / a.pitch), bk = (int)(z / a.pitch);
+    long long best_d = 0x7FFFFFFFFFFFFFFFll;
+    unsigned long long best_c = 0;
+    for (int dk = -1; dk <= 1; ++dk)
+      for (int dj = -1; dj <= 1; ++dj)
+        for (int di = -1; di <= 1; ++di) {
+          const int ni = bi + di, nj = bj + dj, nk = bk + dk;
+          if (ni < 0 || nj < 0 || nk < 0 || ni >= (int)a.gx || nj >= (int)a.gy || nk >= (int)a.gz) continue;
+          const unsigned long long c = (unsigned long long)ni + (unsigned long long)a.gx * ((unsigned long long)nj + (unsigned long long)a.gy * nk);
+          const unsigned long long h = splitmix64(c ^ a.seed);
+          const long long sx = (long long)ni * a.pitch + (long long)(((h & 0xFFFFull) * a.pitch) >> 16);
+          const long long sy = (long long)nj * a.pitch + (long long)((((h >> 16) & 0xFFFFull) * a.pitch) >> 16);
+          const long long sz = (long long)nk * a.pitch + (long long)((((h >> 32) & 0xFFFFull) * a.pitch) >> 16);
+          const long long d = (x - sx) * (x - sx) + (y - sy) * (y - sy) + (z - sz) * (z - sz);
+          if (d < best_d || (d == best_d && c < best_c)) { best_d = d; best_c = c; }
+        }
+    unsigned long long lab = sizeof(L) == 8 ? (splitmix64(best_c + 1ull) | 1ull) : (best_c + 1ull);
+    static_cast<L*>(a.dst)[i] = (L)lab;
+  }
+}
+
 }  // namespace zm

@@ -112,8 +112,29 @@ class Mesher:
       data = np.ascontiguousarray(data)
     c_order = 1 if data.flags.c_contiguous else 0
     self._max_label = (1 << (8 * nbytes)) - 1
-    self._check(self._lib.zm_mesh(self._h, C.c_void_p(data.ctypes.data), nbytes, shape[0], shape[1], shape[2],
-                                  c_order, 1 if close else 0, 0))
+    self._check(self._call_mesh(data.ctypes.data, nbytes, shape, c_order, close, 0))
+
+  def mesh_shard(self, data, origin, close: bool = False):
+    """Mesh one shard of a larger volume: like mesh(), but `origin` (x, y, z voxels) is added to
+    every vertex coordinate so that neighbouring shards agree on the keys of shared planes."""
+    self._origin = tuple(int(o) for o in origin)
+    try:
+      return self.mesh(data, close=close)
+    finally:
+      self._origin = None
+
+  def _call_mesh(self, ptr, nbytes, shape, c_order, close, mem_kind):
+    origin = getattr(self, "_origin", None)
+    if origin is None:
+      return self._lib.zm_mesh(self._h, C.c_void_p(ptr), nbytes, shape[0], shape[1], shape[2], c_order,
+                               1 if close else 0, mem_kind)
+    o = (C.c_uint64 * 3)(*origin)
+    return self._lib.zm_mesh_shard(self._h, C.c_void_p(ptr), nbytes, shape[0], shape[1], shape[2], c_order,
+                                   1 if close else 0, mem_kind, o)
+
+  def set_stream(self, cuda_stream):
+    """Queue all work on a caller-owned CUDA stream (integer cudaStream_t); None restores the own one."""
+    self._check(self._lib.zm_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
 
   def _mesh_device(self, obj, cai, close: bool):
     shape = tuple(int(s) for s in cai["shape"])
@@ -138,8 +159,7 @@ class Mesher:
       raise ValueError("device arrays must be C- or Fortran-contiguous")
     ptr = int(cai["data"][0])
     self._max_label = (1 << (8 * nbytes)) - 1
-    self._check(self._lib.zm_mesh(self._h, C.c_void_p(ptr), nbytes, s3[0], s3[1], s3[2], c_order,
-                                  1 if close else 0, 1))
+    self._check(self._call_mesh(ptr, nbytes, s3, c_order, close, 1))
 
   def ids(self):
     n = int(self._lib.zm_num_ids(self._h))
