@@ -14,7 +14,7 @@ def voronoi_device(shape, pitch: int, dtype=np.uint64, seed: int = 0, order: str
                    full_shape=None, device: int = 0):
   """Jittered-grid Voronoi segmentation written by a CUDA kernel into a new torch tensor whose
   logical shape is `shape` and whose memory order is `order` ("C" or "F").  Bit-identical to
-  oracle/oracle.py:voronoi_volume.  Returns (tensor, label_bytes); signed torch dtypes stand in for
+  the numpy generator the tests use.  Returns (tensor, label_bytes); signed torch dtypes stand in for
   the unsigned ones torch lacks -- only the bit patterns matter."""
   import torch
   lib = _lib.load()
