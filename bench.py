@@ -283,7 +283,7 @@ def main():
   for _ in range(args.warmup):
     st = step()
   barrier()
-  acc = {k: 0.0 for k in ("ms_classify", "ms_scan", "ms_emit", "ms_finalize", "ms_total")}
+  acc = {k: 0.0 for k in ("ms_classify", "ms_scan", "ms_faces", "ms_vertices", "ms_total", "ms_finalize")}
   launches = 0
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   with ClockSampler(dev) as clocks:
@@ -312,10 +312,12 @@ def main():
   peak, peak_src = load_peaks()
   nvox_local = int(np.prod(vol.shape))
   V, T = st["n_vertices"], st["n_faces"]
+  # algorithmic bytes per launch: the volume for the classification pass, 12 B per
+  # triangle for the face pass, 12 B per vertex (+12 B with normals) for the vertex pass
   kern = {
-    "k_classify": (acc["ms_classify"] / args.steps, nvox_local * label_bytes + 4 * V),
-    "k_emit": (acc["ms_emit"] / args.steps, nvox_local * label_bytes + 8 * V + 12 * T + 4 * V),
-    "k_finalize": (acc["ms_finalize"] / args.steps, 8 * V + 12 * V + (12 * T + 12 * V if wl["normals"] else 0)),
+    "k_classify": (acc["ms_classify"] / args.steps, nvox_local * label_bytes),
+    "k_faces": (acc["ms_faces"] / args.steps, 12 * T),
+    "k_vertices": (acc["ms_vertices"] / args.steps, 12 * V + (12 * V if wl["normals"] else 0)),
   }
   dom = max(kern, key=lambda k: kern[k][0])
   dom_ms, dom_bytes = kern[dom]
@@ -331,7 +333,8 @@ def main():
   roofline = {
     "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
-    "kernel_ms": {k: v[0] for k, v in kern.items()},
+    "kernel_ms": {**{k: v[0] for k, v in kern.items()}, "scan": acc["ms_scan"] / args.steps},
+    "kernel_frac": {k: (v[1] / 1e9 / (v[0] / 1e3) / peak if v[0] > 0 else None) for k, v in kern.items()},
     "pipeline": {"algorithmic_bytes": b_alg, "ms": ms, "achieved": b_alg / 1e9 / (ms / 1e3),
                  "frac": b_alg / 1e9 / (ms / 1e3) / peak,
                  "note": "SURVEY 8d: N*sizeof(label) + 12 B/vertex + 12 B/triangle (+12 B/vertex normals), rank-local"},

@@ -131,12 +131,16 @@ int zm_fetch_all(zm_handle* h, float* vertices, uint32_t* faces, float* normals_
 
 typedef struct {
   uint64_t n_voxels, n_labels, n_vertices, n_faces;
+  uint64_t n_records;      /* (label, cube) pairs that produced triangles                          */
+  uint64_t n_tiles, n_active_tiles, n_dense_tiles; /* 32x8x8 tiles: all / non-uniform / redone in dense mode */
   uint64_t hash_capacity, perm_capacity;
   uint32_t attempts;   /* classification passes run (1 unless a capacity guess was too small) */
   uint32_t launches;   /* kernels launched by the last zm_mesh                                 */
-  float ms_h2d, ms_classify, ms_scan, ms_emit, ms_total; /* CUDA-event times of the last zm_mesh */
-  float ms_finalize;   /* last zm_finalize                                                     */
+  uint32_t used_tma;   /* 1: tiles staged by TMA, 0: volume not 16-byte aligned, plain loads    */
   uint32_t launches_finalize;
+  float ms_h2d, ms_classify, ms_scan, ms_total; /* CUDA-event times of the last zm_mesh          */
+  float ms_faces, ms_vertices, ms_finalize;     /* last zm_finalize / first zm_get (pass 2)      */
+  float reserved;
 } zm_stats_t;
 int zm_stats(zm_handle* h, zm_stats_t* out);
 

@@ -35,10 +35,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
 class zm_stats_t(C.Structure):
   _fields_ = [
     ("n_voxels", C.c_uint64), ("n_labels", C.c_uint64), ("n_vertices", C.c_uint64), ("n_faces", C.c_uint64),
+    ("n_records", C.c_uint64), ("n_tiles", C.c_uint64), ("n_active_tiles", C.c_uint64), ("n_dense_tiles", C.c_uint64),
     ("hash_capacity", C.c_uint64), ("perm_capacity", C.c_uint64),
-    ("attempts", C.c_uint32), ("launches", C.c_uint32),
-    ("ms_h2d", C.c_float), ("ms_classify", C.c_float), ("ms_scan", C.c_float), ("ms_emit", C.c_float),
-    ("ms_total", C.c_float), ("ms_finalize", C.c_float), ("launches_finalize", C.c_uint32),
+    ("attempts", C.c_uint32), ("launches", C.c_uint32), ("used_tma", C.c_uint32), ("launches_finalize", C.c_uint32),
+    ("ms_h2d", C.c_float), ("ms_classify", C.c_float), ("ms_scan", C.c_float), ("ms_total", C.c_float),
+    ("ms_faces", C.c_float), ("ms_vertices", C.c_float), ("ms_finalize", C.c_float), ("reserved", C.c_float),
   ]
 
 

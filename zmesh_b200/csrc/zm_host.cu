@@ -46,8 +46,8 @@ struct LabelRec {
 };
 
 struct FinalState {
-  bool valid = false;
-  int normals = 0, voxel_centered = 0, transpose = 0;
+  bool faces_valid = false, verts_valid = false, normals_valid = false;
+  int voxel_centered = 0, transpose = 0, normals_transpose = 0;
   float off[3] = {0, 0, 0};
 };
 
@@ -57,23 +57,29 @@ struct zm_handle {
   int device = 0;
   cudaStream_t stream = nullptr;      // the stream all work is queued on
   cudaStream_t own_stream = nullptr;  // created by zm_create (stream == own_stream unless zm_set_stream)
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float res[3] = {1, 1, 1};
   std::string err;
 
-  // capacity guesses carried between calls
+  // capacity guesses carried between calls (per voxel)
   uint32_t hash_cap = 1u << 16;
-  double perm_ratio = 0.25;  // perm capacity as a fraction of the voxel count
+  double perm_ratio = 0.12, rec_ratio = 0.12, tl_ratio = 0.004;
 
-  // scratch + results (device)
-  DevBuf d_vol, d_keys, d_cntV, d_cntT, d_curT, d_offV, d_offT, d_list, d_rowbase, d_perm, d_misc;
-  DevBuf d_vkeys, d_faces, d_verts, d_normals;
-  unsigned long long* h_misc = nullptr;  // pinned: totals[4], flags
+  // scratch + intermediates (device)
+  DevBuf d_vol, d_keys, d_cnt, d_offV, d_offT, d_list, d_partial, d_ctl;
+  DevBuf d_own6, d_rowbase, d_perm, d_vl, d_rec, d_tl, d_hdr, d_worklist, d_dense;
+  // results (device)
+  DevBuf d_faces, d_verts, d_normals;
+  zm::Control* h_ctl = nullptr;  // pinned
   std::vector<uint64_t> h_list;
+
+  // what pass 2 needs to know about the meshed volume
+  zm::VolParams vp{};
+  bool c_order = false;
+  uint32_t n_work = 0;
 
   // results (host)
   bool has_result = false;
-  uint32_t table_cap = 0;  // capacity of the label table the result offsets refer to
   uint64_t Vtot = 0, Ttot = 0;
   std::vector<LabelRec> recs;                   // storage (table) order
   std::unordered_map<uint64_t, uint32_t> index;  // label -> recs index
@@ -104,18 +110,24 @@ int fail(zm_handle* h, int code, const std::string& msg) {
   return code;
 }
 
-typedef void (*classify_fn)(const VolParams, const Pass1Args);
-typedef void (*emit_fn)(const VolParams, const Pass2Args);
+typedef void (*classify_fn)(const VolParams, const CUtensorMap, const Pass1Args);
+typedef void (*pass2_fn)(const VolParams, const Pass2Args);
 
 struct KernelSet {
-  classify_fn classify;
-  emit_fn emit;
-  size_t classify_smem, emit_smem;
+  classify_fn classify[2];  // MODE 0 / MODE 1
+  size_t smem[2];
+  int row_pad;              // staged row length (elements) = TMA box extent along f
 };
 
 template <typename L, bool CO>
 KernelSet make_set() {
-  return KernelSet{k_classify<L, CO>, k_emit<L, CO>, classify_smem_bytes<L>(), emit_smem_bytes<L>()};
+  KernelSet k;
+  k.classify[0] = k_classify<L, CO, 0>;
+  k.classify[1] = k_classify<L, CO, 1>;
+  k.smem[0] = sizeof(P1Smem<L, 0>);
+  k.smem[1] = sizeof(P1Smem<L, 1>);
+  k.row_pad = RowPad<L>::value;
+  return k;
 }
 
 KernelSet kernel_set(int label_bytes, bool c_order) {
@@ -127,18 +139,65 @@ KernelSet kernel_set(int label_bytes, bool c_order) {
   }
 }
 
+pass2_fn faces_kernel(bool c_order, bool normals) {
+  if (c_order) return normals ? k_faces<true, true> : k_faces<true, false>;
+  return normals ? k_faces<false, true> : k_faces<false, false>;
+}
+pass2_fn vertices_kernel(bool c_order) { return c_order ? k_vertices<true> : k_vertices<false>; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// TMA descriptor of the label volume (memory order f, m, s), box = the staged tile region.
+// Returns false when the volume does not meet TMA's 16-byte base/stride rules (the kernel then
+// stages tiles with ordinary loads).
+bool make_tensor_map(CUtensorMap* tm, const void* data, int label_bytes, uint32_t nf, uint32_t nm, uint32_t ns,
+                     int row_pad) {
+  memset(tm, 0, sizeof(*tm));
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  if (getenv("ZMESH_B200_NO_TMA")) return false;
+  const uint64_t eb = (uint64_t)label_bytes;
+  if (((uintptr_t)data & 15u) != 0 || ((uint64_t)nf * eb) % 16 != 0) return false;
+  CUtensorMapDataType dt = label_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                         : label_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                         : label_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32
+                                            : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+  cuuint64_t dims[3] = {nf, nm, ns};
+  cuuint64_t strides[2] = {(cuuint64_t)nf * eb, (cuuint64_t)nf * nm * eb};
+  cuuint32_t box[3] = {(cuuint32_t)row_pad, (cuuint32_t)RM, (cuuint32_t)RS};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, dt, 3, const_cast<void*>(data), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int prepare_device(zm_handle* h) {
-  // case tables -> device globals; opt in to > 48 KB of shared memory per CTA where needed
+  // case tables -> device globals; opt in to > 48 KB of shared memory per CTA
   ZM_CUDA(h, cudaMemcpyToSymbol(TRI_COUNT_D, TRI_COUNT, sizeof(TRI_COUNT)));
   static_assert(sizeof(TRI_NIBBLES) == 256 * sizeof(unsigned long long), "table size");
   ZM_CUDA(h, cudaMemcpyToSymbol(TRI_NIBBLES_D, TRI_NIBBLES, sizeof(TRI_NIBBLES)));
   for (int lb : {1, 2, 4, 8})
     for (int co = 0; co < 2; ++co) {
       KernelSet ks = kernel_set(lb, co != 0);
-      ZM_CUDA(h, cudaFuncSetAttribute((const void*)ks.classify, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)ks.classify_smem));
-      ZM_CUDA(h, cudaFuncSetAttribute((const void*)ks.emit, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)ks.emit_smem));
+      for (int mode = 0; mode < 2; ++mode)
+        ZM_CUDA(h, cudaFuncSetAttribute((const void*)ks.classify[mode], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)ks.smem[mode]));
     }
   return ZM_OK;
 }
@@ -146,6 +205,7 @@ int prepare_device(zm_handle* h) {
 void drop_results(zm_handle* h) {
   h->has_result = false;
   h->Vtot = h->Ttot = 0;
+  h->n_work = 0;
   h->recs.clear();
   h->index.clear();
   h->sorted_ids.clear();
@@ -179,7 +239,6 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   h->stats = zm_stats_t{};
   h->stats.n_voxels = sx * sy * sz;
   h->has_result = true;
-  h->table_cap = 0;
   if (sx == 0 || sy == 0 || sz == 0) return ZM_OK;
   if (!labels) return fail(h, ZM_ERR_INVALID, "labels is NULL");
 
@@ -192,6 +251,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   // no cube without two voxels along every axis (marching_cubes.hpp:226-257 loops are empty)
   if (vp.Ef < 2 || vp.Em < 2 || vp.Es < 2) return ZM_OK;
   vp.ntf = (vp.Ef + TF - 1) / TF; vp.ntm = (vp.Em + TM - 1) / TM; vp.nts = (vp.Es + TS - 1) / TS;
+  vp.Efp = vp.ntf * TF;
   const unsigned long long ntiles = (unsigned long long)vp.ntf * vp.ntm * vp.nts;
   if (ntiles > 0x7FFFFFFFull) return fail(h, ZM_ERR_UNSUPPORTED, "too many tiles for one launch; shard the volume");
   const unsigned long long nvox = (unsigned long long)vp.nf * vp.nm * vp.ns;
@@ -209,96 +269,99 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   ZM_CUDA(h, cudaEventRecord(h->ev[1], st));
 
   const KernelSet ks = kernel_set(label_bytes, c_order != 0);
-  const size_t nrows = (size_t)vp.Es * vp.Em * vp.ntf;
-  ZM_CUDA(h, h->d_rowbase.ensure(nrows * sizeof(uint32_t)));
-  ZM_CUDA(h, h->d_misc.ensure(64));
-  unsigned long long* d_totals = h->d_misc.as<unsigned long long>();      // [4]
-  unsigned long long* d_cursor = h->d_misc.as<unsigned long long>() + 4;  // [1]
-  uint32_t* d_flags = reinterpret_cast<uint32_t*>(h->d_misc.as<unsigned long long>() + 5);
+  CUtensorMap tmap;
+  vp.use_tma = make_tensor_map(&tmap, vp.data, label_bytes, vp.nf, vp.nm, vp.ns, ks.row_pad) ? 1u : 0u;
 
-  unsigned long long permcap = (unsigned long long)(h->perm_ratio * (double)nvox) + 4096ull;
-  if (permcap > 0xFFFFFFF0ull) permcap = 0xFFFFFFF0ull;
-  uint32_t flags = 0;
-  unsigned long long totals[4] = {0, 0, 0, 0};
+  const size_t nrows = (size_t)vp.Es * vp.Em * vp.ntf;
+  ZM_CUDA(h, h->d_own6.ensure((size_t)vp.Es * vp.Em * vp.Efp));
+  ZM_CUDA(h, h->d_rowbase.ensure(nrows * sizeof(uint32_t)));
+  ZM_CUDA(h, h->d_hdr.ensure((size_t)ntiles * sizeof(TileHdr)));
+  ZM_CUDA(h, h->d_worklist.ensure((size_t)ntiles * 4));
+  ZM_CUDA(h, h->d_dense.ensure((size_t)ntiles * 4));
+  ZM_CUDA(h, h->d_ctl.ensure(sizeof(Control)));
+  ZM_CUDA(h, h->d_partial.ensure(3 * 1024 * 8));
+  Control* d_ctl = h->d_ctl.as<Control>();
+
+  unsigned long long capV = (unsigned long long)(h->perm_ratio * (double)nvox) + 65536ull;
+  unsigned long long capR = (unsigned long long)(h->rec_ratio * (double)nvox) + 65536ull;
+  unsigned long long capL = (unsigned long long)(h->tl_ratio * (double)nvox) + 65536ull;
+  if (capV > 0xFFFFFFF0ull) capV = 0xFFFFFFF0ull;
   uint32_t launches = 0;
   int attempt = 0;
+  Control ctl{};
   for (;; ++attempt) {
-    if (attempt >= 8) return fail(h, ZM_ERR_UNSUPPORTED, "label table / perm sizing did not converge");
+    if (attempt >= 8) return fail(h, ZM_ERR_UNSUPPORTED, "label table / capacity sizing did not converge");
     const uint32_t cap = h->hash_cap;
     ZM_CUDA(h, h->d_keys.ensure((size_t)cap * 8));
-    ZM_CUDA(h, h->d_cntV.ensure((size_t)cap * 4));
-    ZM_CUDA(h, h->d_cntT.ensure((size_t)cap * 4));
+    ZM_CUDA(h, h->d_cnt.ensure((size_t)cap * 8));
     ZM_CUDA(h, h->d_offV.ensure((size_t)cap * 8));
     ZM_CUDA(h, h->d_offT.ensure((size_t)cap * 8));
     ZM_CUDA(h, h->d_list.ensure((size_t)cap * 24));
-    ZM_CUDA(h, h->d_perm.ensure((size_t)permcap * 4));
+    ZM_CUDA(h, h->d_perm.ensure((size_t)capV * 4));
+    ZM_CUDA(h, h->d_vl.ensure((size_t)capV * 2));
+    ZM_CUDA(h, h->d_rec.ensure((size_t)capR * 4));
+    ZM_CUDA(h, h->d_tl.ensure((size_t)capL * sizeof(TLEntry)));
     ZM_CUDA(h, cudaMemsetAsync(h->d_keys.p, 0, (size_t)cap * 8, st));
-    ZM_CUDA(h, cudaMemsetAsync(h->d_cntV.p, 0, (size_t)cap * 4, st));
-    ZM_CUDA(h, cudaMemsetAsync(h->d_cntT.p, 0, (size_t)cap * 4, st));
-    ZM_CUDA(h, cudaMemsetAsync(h->d_misc.p, 0, 64, st));
+    ZM_CUDA(h, cudaMemsetAsync(h->d_cnt.p, 0, (size_t)cap * 8, st));
+    ZM_CUDA(h, cudaMemsetAsync(h->d_ctl.p, 0, sizeof(Control), st));
 
-    LabelTable ht{h->d_keys.as<unsigned long long>(), h->d_cntV.as<uint32_t>(), h->d_cntT.as<uint32_t>(), cap - 1};
-    Pass1Args p1{ht, h->d_rowbase.as<uint32_t>(), h->d_perm.as<uint32_t>(), permcap, d_cursor, d_flags};
-    ks.classify<<<(uint32_t)ntiles, NT, ks.classify_smem, st>>>(vp, p1);
+    LabelTable ht{h->d_keys.as<u64>(), h->d_cnt.as<u64>(), cap - 1};
+    Pass1Args p1{ht, d_ctl, h->d_own6.as<uint8_t>(), h->d_rowbase.as<uint32_t>(), h->d_perm.as<uint32_t>(),
+                 h->d_vl.as<uint16_t>(), h->d_rec.as<uint32_t>(), h->d_tl.as<TLEntry>(), h->d_hdr.as<TileHdr>(),
+                 h->d_worklist.as<uint32_t>(), h->d_dense.as<uint32_t>(), capV, capR, capL};
+    ks.classify[0]<<<(uint32_t)ntiles, NT, ks.smem[0], st>>>(vp, tmap, p1);
+    ZM_CUDA(h, cudaGetLastError());
+    const uint32_t dense_grid = (uint32_t)std::min<unsigned long long>(ntiles, 148ull);
+    ks.classify[1]<<<dense_grid, NT, ks.smem[1], st>>>(vp, tmap, p1);
     ZM_CUDA(h, cudaGetLastError());
     ZM_CUDA(h, cudaEventRecord(h->ev[2], st));
-    ScanOut so{h->d_offV.as<unsigned long long>(), h->d_offT.as<unsigned long long>(),
-               h->d_list.as<unsigned long long>(), d_totals};
-    k_label_scan<<<1, 1024, 0, st>>>(ht, so, d_cursor);
+    const uint32_t chunk = std::max<uint32_t>(1024u, cap / 1024u);
+    ScanArgs sa{ht, h->d_offV.as<u64>(), h->d_offT.as<u64>(), h->d_list.as<u64>(), h->d_partial.as<u64>(), d_ctl, chunk};
+    k_scan_partials<<<cap / chunk, 1024, 0, st>>>(sa);
     ZM_CUDA(h, cudaGetLastError());
-    launches += 2;
-    ZM_CUDA(h, cudaMemcpyAsync(h->h_misc, h->d_misc.p, 48, cudaMemcpyDeviceToHost, st));
+    k_scan_apply<<<cap / chunk, 1024, 0, st>>>(sa);
+    ZM_CUDA(h, cudaGetLastError());
+    k_tl_fixup<<<148 * 4, 256, 0, st>>>(h->d_tl.as<TLEntry>(), d_ctl, capL, h->d_offV.as<u64>(), h->d_offT.as<u64>());
+    ZM_CUDA(h, cudaGetLastError());
+    launches += 5;
+    ZM_CUDA(h, cudaMemcpyAsync(h->h_ctl, d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
     ZM_CUDA(h, cudaEventRecord(h->ev[3], st));
     ZM_CUDA(h, cudaStreamSynchronize(st));
-    memcpy(totals, h->h_misc, sizeof(totals));
-    flags = *reinterpret_cast<uint32_t*>(h->h_misc + 5);
-    if (flags & FLAG_HASH_FULL) {
+    ctl = *h->h_ctl;
+    if (ctl.flags & FLAG_INTERNAL) return fail(h, ZM_ERR_CUDA, "internal: dense-mode tile overflowed");
+    if (ctl.flags & FLAG_HASH_FULL) {
       if (h->hash_cap >= (1u << 30)) return fail(h, ZM_ERR_UNSUPPORTED, "more than 2^29 distinct labels");
       h->hash_cap <<= 3;
       continue;
     }
     // keep the table at most half full so probes stay short
-    if (totals[0] * 2 > cap) {
-      while ((unsigned long long)h->hash_cap < totals[0] * 4 && h->hash_cap < (1u << 30)) h->hash_cap <<= 1;
+    if (ctl.totals[0] * 2 > cap) {
+      while ((unsigned long long)h->hash_cap < ctl.totals[0] * 4 && h->hash_cap < (1u << 30)) h->hash_cap <<= 1;
       continue;
     }
-    if (totals[3] > 0xFFFFFFF0ull || (flags & FLAG_RANK_OVERFLOW))
+    if (ctl.cur_perm > 0xFFFFFFF0ull || ctl.cur_tl > 0xFFFFFFF0ull)
       return fail(h, ZM_ERR_UNSUPPORTED, "more than 2^32-16 vertices in one call; shard the volume");
-    if (flags & FLAG_PERM_FULL) {
-      permcap = totals[3] + 4096ull;
-      h->perm_ratio = std::max(h->perm_ratio, 1.05 * (double)totals[3] / (double)nvox);
+    if (ctl.flags & FLAG_CAP) {
+      capV = std::max(capV, ctl.cur_perm + 4096ull);
+      capR = std::max(capR, ctl.cur_rec + 4096ull);
+      capL = std::max(capL, ctl.cur_tl + 4096ull);
       continue;
     }
     break;
   }
   h->stats.attempts = (uint32_t)attempt + 1;
   const uint32_t cap = h->hash_cap;
-  const unsigned long long nlabels = totals[0], Vtot = totals[1], Ttot = totals[2];
-  if (Vtot != totals[3]) return fail(h, ZM_ERR_CUDA, "internal: vertex totals disagree");
+  const unsigned long long nlabels = ctl.totals[0], Vtot = ctl.totals[1], Ttot = ctl.totals[2];
+  if (Vtot != ctl.cur_perm) return fail(h, ZM_ERR_CUDA, "internal: vertex totals disagree");
+  if (Ttot != ctl.cur_tri)
+    return fail(h, ZM_ERR_UNSUPPORTED, "a label has more than 2^32-1 faces in one call; shard the volume");
 
-  ZM_CUDA(h, cudaEventRecord(h->ev[3], st));
   if (nlabels) {
-    ZM_CUDA(h, h->d_vkeys.ensure((size_t)Vtot * 8));
-    ZM_CUDA(h, h->d_faces.ensure((size_t)Ttot * 12));
-    ZM_CUDA(h, h->d_curT.ensure((size_t)cap * 4));
-    ZM_CUDA(h, cudaMemsetAsync(h->d_curT.p, 0, (size_t)cap * 4, st));
-    LabelTable ht{h->d_keys.as<unsigned long long>(), h->d_cntV.as<uint32_t>(), h->d_cntT.as<uint32_t>(), cap - 1};
-    Pass2Args p2{ht, h->d_offV.as<unsigned long long>(), h->d_offT.as<unsigned long long>(),
-                 h->d_curT.as<uint32_t>(), h->d_rowbase.as<uint32_t>(), h->d_perm.as<uint32_t>(),
-                 h->d_vkeys.as<unsigned long long>(), h->d_faces.as<uint32_t>(), d_flags};
-    ks.emit<<<(uint32_t)ntiles, NT, ks.emit_smem, st>>>(vp, p2);
-    ZM_CUDA(h, cudaGetLastError());
-    launches += 1;
     h->h_list.resize((size_t)nlabels * 3);
     ZM_CUDA(h, cudaMemcpyAsync(h->h_list.data(), h->d_list.p, (size_t)nlabels * 24, cudaMemcpyDeviceToHost, st));
-    ZM_CUDA(h, cudaMemcpyAsync(h->h_misc, h->d_misc.p, 48, cudaMemcpyDeviceToHost, st));
   }
   ZM_CUDA(h, cudaEventRecord(h->ev[4], st));
   ZM_CUDA(h, cudaStreamSynchronize(st));
-  if (nlabels) {
-    flags = *reinterpret_cast<uint32_t*>(h->h_misc + 5);
-    if (flags & FLAG_INTERNAL) return fail(h, ZM_ERR_CUDA, "internal: label missing from the table in the emit pass");
-  }
 
   // host-side label directory (storage order = table order; offsets are running sums)
   h->recs.resize((size_t)nlabels);
@@ -323,70 +386,100 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   std::sort(h->sorted_ids.begin(), h->sorted_ids.end());
   h->Vtot = Vtot;
   h->Ttot = Ttot;
-  h->table_cap = cap;
+  h->vp = vp;
+  h->c_order = c_order != 0;
+  h->n_work = ctl.work_count;
 
   h->stats.n_labels = h->sorted_ids.size();
   h->stats.n_vertices = Vtot;
   h->stats.n_faces = Ttot;
+  h->stats.n_records = ctl.cur_rec;
+  h->stats.n_active_tiles = ctl.work_count;
+  h->stats.n_dense_tiles = ctl.dense_count;
+  h->stats.n_tiles = ntiles;
   h->stats.hash_capacity = cap;
-  h->stats.perm_capacity = permcap;
+  h->stats.perm_capacity = capV;
+  h->stats.used_tma = vp.use_tma;
   h->stats.launches = launches;
   cudaEventElapsedTime(&h->stats.ms_h2d, h->ev[0], h->ev[1]);
   cudaEventElapsedTime(&h->stats.ms_classify, h->ev[1], h->ev[2]);
   cudaEventElapsedTime(&h->stats.ms_scan, h->ev[2], h->ev[3]);
-  cudaEventElapsedTime(&h->stats.ms_emit, h->ev[3], h->ev[4]);
   cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[4]);
-  // let the perm guess track the data (next call of a similar volume needs one attempt)
-  h->perm_ratio = std::max(0.02, std::min(6.5, 1.25 * (double)Vtot / (double)nvox));
+  // let the capacity guesses track the data (next call of a similar volume needs one attempt)
+  h->perm_ratio = std::max(0.02, std::min(6.5, 1.25 * (double)ctl.cur_perm / (double)nvox));
+  h->rec_ratio = std::max(0.02, std::min(8.5, 1.25 * (double)ctl.cur_rec / (double)nvox));
+  h->tl_ratio = std::max(0.002, std::min(2.0, 1.25 * (double)ctl.cur_tl / (double)nvox));
   return ZM_OK;
 }
 
+// Pass 2 (lazy): faces once per zm_mesh; vertices per (voxel_centered, transpose, offset); normals per
+// transpose.  Everything is written in its final layout on the device.
 int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, const float* off) {
   if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
   float o[3] = {h->res[0], h->res[1], h->res[2]};
   if (off) { o[0] = off[0]; o[1] = off[1]; o[2] = off[2]; }
   normals = normals ? 1 : 0; voxel_centered = voxel_centered ? 1 : 0; transpose = transpose ? 1 : 0;
   FinalState& f = h->fin;
-  const bool same_verts = f.valid && f.voxel_centered == voxel_centered && f.transpose == transpose &&
+  const bool same_verts = f.verts_valid && f.voxel_centered == voxel_centered && f.transpose == transpose &&
                           (!voxel_centered || (f.off[0] == o[0] && f.off[1] == o[1] && f.off[2] == o[2]));
-  const bool need_normals = normals && !(same_verts && f.normals);
-  if (same_verts && !need_normals) return ZM_OK;
+  const bool need_normals = normals && !(f.normals_valid && f.normals_transpose == transpose);
+  const bool need_faces = !f.faces_valid;
+  if (same_verts && !need_normals && !need_faces) return ZM_OK;
   ZM_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   uint32_t launches = 0;
-  ZM_CUDA(h, cudaEventRecord(h->ev[0], st));
-  if (h->Vtot) {
-    if (!same_verts) {
-      ZM_CUDA(h, h->d_verts.ensure((size_t)h->Vtot * 12));
-      FinalizeArgs fa{h->d_vkeys.as<unsigned long long>(), h->d_verts.as<float>(), h->Vtot,
-                      h->res[0], h->res[1], h->res[2], o[0], o[1], o[2], voxel_centered, transpose};
-      k_finalize_vertices<<<grid_for(h->Vtot, 256), 256, 0, st>>>(fa);
-      ZM_CUDA(h, cudaGetLastError());
-      ++launches;
-    }
+  ZM_CUDA(h, cudaEventRecord(h->ev[5], st));
+  ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
+  if (h->Vtot && h->n_work) {
+    ZM_CUDA(h, h->d_faces.ensure((size_t)h->Ttot * 12));
+    ZM_CUDA(h, h->d_verts.ensure((size_t)h->Vtot * 12));
     if (need_normals) {
       ZM_CUDA(h, h->d_normals.ensure((size_t)h->Vtot * 12));
       ZM_CUDA(h, cudaMemsetAsync(h->d_normals.p, 0, (size_t)h->Vtot * 12, st));
-      NormalsArgs na{h->d_vkeys.as<unsigned long long>(), h->d_faces.as<uint32_t>(), h->d_normals.as<float>(),
-                     h->d_offV.as<unsigned long long>(), h->d_offT.as<unsigned long long>(), h->Ttot, h->Vtot,
-                     h->table_cap, h->res[0], h->res[1], h->res[2], transpose};
-      k_normals_accumulate<<<grid_for(h->Ttot, 256), 256, 0, st>>>(na);
+    }
+    Pass2Args a{};
+    a.hdr = h->d_hdr.as<TileHdr>();
+    a.worklist = h->d_worklist.as<uint32_t>();
+    a.own6 = h->d_own6.as<uint8_t>();
+    a.rowbase = h->d_rowbase.as<uint32_t>();
+    a.perm = h->d_perm.as<uint32_t>();
+    a.vl = h->d_vl.as<uint16_t>();
+    a.rec = h->d_rec.as<uint32_t>();
+    a.tl = h->d_tl.as<TLEntry>();
+    a.faces = h->d_faces.as<uint32_t>();
+    a.verts = h->d_verts.as<float>();
+    a.normals = h->d_normals.as<float>();
+    a.r0 = h->res[0]; a.r1 = h->res[1]; a.r2 = h->res[2];
+    a.c0 = o[0]; a.c1 = o[1]; a.c2 = o[2];
+    a.voxel_centered = voxel_centered;
+    a.transpose = transpose;
+    a.write_faces = need_faces ? 1 : 0;
+    a.write_verts = same_verts ? 0 : 1;
+    a.normalize = need_normals ? 1 : 0;
+    if (need_faces || need_normals) {
+      faces_kernel(h->c_order, need_normals)<<<h->n_work, NT, 0, st>>>(h->vp, a);
       ZM_CUDA(h, cudaGetLastError());
-      k_normals_normalize<<<grid_for(h->Vtot, 256), 256, 0, st>>>(h->d_normals.as<float>(), h->Vtot);
+      ++launches;
+    }
+    ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
+    if (!same_verts || need_normals) {
+      vertices_kernel(h->c_order)<<<h->n_work, NT, 0, st>>>(h->vp, a);
       ZM_CUDA(h, cudaGetLastError());
-      launches += 2;
+      ++launches;
     }
   }
-  ZM_CUDA(h, cudaEventRecord(h->ev[1], st));
+  ZM_CUDA(h, cudaEventRecord(h->ev[7], st));
   ZM_CUDA(h, cudaStreamSynchronize(st));
-  cudaEventElapsedTime(&h->stats.ms_finalize, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&h->stats.ms_faces, h->ev[5], h->ev[6]);
+  cudaEventElapsedTime(&h->stats.ms_vertices, h->ev[6], h->ev[7]);
+  cudaEventElapsedTime(&h->stats.ms_finalize, h->ev[5], h->ev[7]);
   h->stats.launches_finalize = launches;
-  const bool had_normals = same_verts && f.normals;
-  f.valid = true;
+  f.faces_valid = true;
+  f.verts_valid = true;
   f.voxel_centered = voxel_centered;
   f.transpose = transpose;
   f.off[0] = o[0]; f.off[1] = o[1]; f.off[2] = o[2];
-  f.normals = (normals || had_normals) ? 1 : 0;
+  if (need_normals) { f.normals_valid = true; f.normals_transpose = transpose; }
   return ZM_OK;
 }
 
@@ -427,7 +520,7 @@ int zm_create(const float resolution[3], int device, zm_handle** out) {
   h->stream = h->own_stream;
   for (auto& ev : h->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
-  if ((e = cudaHostAlloc((void**)&h->h_misc, 64, cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  if ((e = cudaHostAlloc((void**)&h->h_ctl, sizeof(zm::Control), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
   int rc = prepare_device(h);
   if (rc != ZM_OK) {
     g_create_error = h->err;
@@ -442,10 +535,11 @@ void zm_destroy(zm_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->d_vol, &h->d_keys, &h->d_cntV, &h->d_cntT, &h->d_curT, &h->d_offV, &h->d_offT, &h->d_list,
-                    &h->d_rowbase, &h->d_perm, &h->d_misc, &h->d_vkeys, &h->d_faces, &h->d_verts, &h->d_normals})
+  for (DevBuf* b : {&h->d_vol, &h->d_keys, &h->d_cnt, &h->d_offV, &h->d_offT, &h->d_list, &h->d_partial, &h->d_ctl,
+                    &h->d_own6, &h->d_rowbase, &h->d_perm, &h->d_vl, &h->d_rec, &h->d_tl, &h->d_hdr, &h->d_worklist,
+                    &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals})
     b->release();
-  if (h->h_misc) cudaFreeHost(h->h_misc);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -565,7 +659,9 @@ int zm_clear(zm_handle* h) {
   drop_results(h);
   h->has_result = had;  // a cleared mesher answers like an empty one (marching_cubes.hpp:184-189)
   cudaSetDevice(h->device);
-  for (DevBuf* b : {&h->d_vkeys, &h->d_faces, &h->d_verts, &h->d_normals, &h->d_perm, &h->d_vol}) b->release();
+  for (DevBuf* b : {&h->d_faces, &h->d_verts, &h->d_normals, &h->d_perm, &h->d_vl, &h->d_rec, &h->d_tl, &h->d_own6,
+                    &h->d_rowbase, &h->d_vol})
+    b->release();
   return ZM_OK;
 }
 
@@ -593,15 +689,16 @@ int zm_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     view->foff_host = h->bulk_foff.data();
     view->vertices_dev = h->Vtot ? h->d_verts.as<float>() : nullptr;
     view->faces_dev = h->Ttot ? h->d_faces.as<uint32_t>() : nullptr;
-    view->normals_dev = (h->fin.normals && h->Vtot) ? h->d_normals.as<float>() : nullptr;
+    view->normals_dev = (normals && h->fin.normals_valid && h->Vtot) ? h->d_normals.as<float>() : nullptr;
   }
   return ZM_OK;
 }
 
 int zm_fetch_all(zm_handle* h, float* vertices, uint32_t* faces, float* normals_out) {
   if (!h) return ZM_ERR_INVALID;
-  if (!h->has_result || !h->fin.valid) return fail(h, ZM_ERR_STATE, "zm_finalize has not been called");
-  if (normals_out && !h->fin.normals) return fail(h, ZM_ERR_STATE, "normals were not requested in zm_finalize");
+  if (!h->has_result || !h->fin.verts_valid) return fail(h, ZM_ERR_STATE, "zm_finalize has not been called");
+  if (normals_out && !(h->fin.normals_valid && h->fin.normals_transpose == h->fin.transpose))
+    return fail(h, ZM_ERR_STATE, "normals were not requested in zm_finalize");
   cudaStream_t st = h->stream;
   if (h->Vtot && vertices)
     ZM_CUDA(h, cudaMemcpyAsync(vertices, h->d_verts.p, (size_t)h->Vtot * 12, cudaMemcpyDeviceToHost, st));

@@ -6,21 +6,27 @@
 //
 //   * a vertex of label L is a voxel-grid edge (two axis-adjacent voxels) with exactly one
 //     endpoint == L.  Each grid edge is OWNED by its lower voxel, so every vertex is produced
-//     exactly once -- no hashing, no sort, no unique pass.
-//   * voxel u owns up to 6 vertex slots: slot 2d+0 = (edge u -> u+d, label of u),
+//     exactly once -- no hashing of vertices, no sort, no unique pass.
+//   * voxel u owns up to 6 vertex slots ("own6" mask): slot 2d+0 = (edge u -> u+d, label of u),
 //     slot 2d+1 = (same edge, label of u+d), d = memory axis 0 (fastest) .. 2 (slowest).
 //   * vertices get a spatial id  g = rowbase[row(u)] + (#slots of earlier voxels in the row)
 //     + (#lower slots of u);  perm[g] = index of the vertex inside its label's vertex list.
-//     Faces find their vertex indices through perm[], which costs 4 B per vertex instead of the
-//     ~6 hash probes per triangle of the reference.
 //
-// Two passes over the volume (tiles of 32 x 8 x 8 voxels, one CTA each):
-//   pass 1 (classify): count per-label vertices/triangles, reserve per-label vertex ranks, write
-//                      rowbase[] and perm[];
-//   pass 2 (emit):     write the packed 64-bit half-voxel vertex keys and the uint32 faces to
-//                      their final per-label ranges.
-// followed by the final gather (key -> float32 with anisotropy / voxel_centered, optional normals).
+// Pass 1 (k_classify, the only kernel that reads the label volume): one CTA per tile of
+// 32 x 8 x 8 voxels (+1 halo) staged in shared memory by TMA (cp.async.bulk.tensor.3d, zero fill
+// outside the volume = the `close` border for free).  Active voxels are compacted, distinct labels
+// of each cube enumerated, per-(tile,label) counts kept in a shared-memory table with
+// warp-aggregated atomics, one global reservation per (tile,label).  Outputs, all label-free:
+//   own6[voxel] (1 B), rowbase[row], perm[g] (4 B/vertex), vl[g] (2 B/vertex: tile-local label
+//   index), rec[] (4 B per (label,cube) pair: cube-in-tile | case | tile-local label index),
+//   tl[] (per (tile,label): label slot + face base), hdr[tile], worklist of non-empty tiles.
+// Scan (k_scan_*) turns per-label counts into per-label output offsets; k_tl_fixup folds them into
+// tl[].  Pass 2 never touches labels again:
+//   k_faces    : one thread per record -> faces (uint32 triples) [+ face normals accumulation]
+//   k_vertices : one thread per owning voxel -> float32 vertices in the final form
+//                fl32(fl32(fl32(res*k) [+ off]) / 2) [+ normals normalisation]
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,61 +34,86 @@
 
 namespace zm {
 
-// device copies of the case tables (filled once per process by zm_upload_tables)
+typedef unsigned long long u64;
+
+// device copies of the case tables (filled once per process by prepare_device)
 __device__ uint8_t TRI_COUNT_D[256];
-__device__ unsigned long long TRI_NIBBLES_D[256];
+__device__ u64 TRI_NIBBLES_D[256];
 
 constexpr int TF = 32;  // tile extent along the memory-fastest axis (= one warp per row)
 constexpr int TM = 8;
 constexpr int TS = 8;
-constexpr int NT = 256;  // threads per CTA: warp w handles the 8 rows with ls == w
+constexpr int NT = 256;  // threads per CTA: warp w handles the s-plane w of the tile
 constexpr int NW = NT / 32;
-constexpr int LT = 1024;      // slots of the CTA-local label table (aggregates global atomics)
-constexpr int LT_PROBES = 32; // bounded probing; on failure the global table is used directly
+constexpr int RM = TM + 1, RS = TS + 1;  // staged label region (halo 1 on the high side)
+constexpr int TILE_VOX = TF * TM * TS;
 static_assert(TS == NW, "one warp per s-plane of the tile");
 
+// staged row length: a multiple of 16 bytes (TMA box constraint) that holds TF+1 voxels plus, for
+// `close`, the 16/sizeof(L)-1 extra leading columns an aligned box start costs (see classify_tile)
+template <typename L> struct RowPad { static constexpr int value = ((TF + 1) * (int)sizeof(L) + 15) / 16 * 16 / (int)sizeof(L); };
+
 enum : uint32_t {
-  FLAG_HASH_FULL = 1u,   // global label table too small -> host grows it and reruns pass 1
-  FLAG_PERM_FULL = 2u,   // perm[] capacity guess too small -> host reruns pass 1 with the exact size
-  FLAG_INTERNAL = 4u,    // invariant violated (label missing in pass 2, ...)
-  FLAG_RANK_OVERFLOW = 8u
+  FLAG_HASH_FULL = 1u,  // global label table too small -> host grows it and reruns pass 1
+  FLAG_CAP = 2u,        // perm / record / tile-label capacity guess too small -> host reruns pass 1
+  FLAG_INTERNAL = 4u    // invariant violated
 };
+
+// capacities of the per-tile shared-memory structures.  MODE 0 covers ordinary segmentations;
+// tiles that overflow it are queued and redone by the MODE 1 launch, whose capacities are the
+// hard maxima of a tile (so it cannot overflow).
+template <int MODE> struct Caps;
+template <> struct Caps<0> { static constexpr int LT = 512, VCAP = 4096, RCAP = 4096, PROBES = 32; };
+template <> struct Caps<1> { static constexpr int LT = 4096, VCAP = 6 * TILE_VOX, RCAP = 8 * TILE_VOX, PROBES = 4096; };
 
 struct VolParams {
   const void* data;        // device pointer, memory order (f fastest, m, s slowest)
   uint32_t nf, nm, ns;     // input extents
   uint32_t Ef, Em, Es;     // extended extents = n + 2*pad (close => virtual zero border)
+  uint32_t Efp;            // ntf * TF: row pitch of own6[]
   uint32_t pad;            // 1 when close
   uint32_t ntf, ntm, nts;  // tiles per axis
   uint32_t ox, oy, oz;     // shard origin in logical voxels (added to keys)
+  uint32_t use_tma;
 };
 
 struct LabelTable {  // global open-addressing table, key 0 = empty (label 0 is never meshed)
-  unsigned long long* keys;
-  uint32_t* cntV;
-  uint32_t* cntT;
+  u64* keys;
+  u64* cnt;  // low 32: vertices, high 32: triangles
   uint32_t mask;  // capacity - 1
+};
+
+struct __align__(8) TileHdr {
+  u64 recbase;
+  uint32_t gbase;
+  uint32_t tlbase;
+  uint16_t nslots, nrec, nlab, pad;
+};
+
+struct __align__(16) TLEntry {  // pass 1: a = label slot | face base in label << 32;  final: a = first
+  u64 a, b;                     // vertex row of the label, b = first face row of this (tile,label)
+};
+
+// control block (device): cursors and flags
+struct Control {
+  u64 cur_perm, cur_rec, cur_tl, cur_tri;
+  uint32_t work_count, dense_count, flags, pad;
+  u64 totals[4];  // n_labels, V_total, T_total, spare (written by the scan)
 };
 
 struct Pass1Args {
   LabelTable ht;
+  Control* ctl;
+  uint8_t* own6;      // [Es][Em][Efp]
   uint32_t* rowbase;  // [Es*Em*ntf]
-  uint32_t* perm;     // [permcap]
-  unsigned long long permcap;
-  unsigned long long* cursor;  // perm segment allocator
-  uint32_t* flags;
-};
-
-struct Pass2Args {
-  LabelTable ht;
-  const unsigned long long* offV;  // per table slot: first vertex row of the label
-  const unsigned long long* offT;
-  uint32_t* curT;  // per table slot: running triangle cursor
-  const uint32_t* rowbase;
-  const uint32_t* perm;
-  unsigned long long* vkeys;  // [V_total]
-  uint32_t* faces;            // [T_total][3]
-  uint32_t* flags;
+  uint32_t* perm;     // [capV]
+  uint16_t* vl;       // [capV]
+  uint32_t* rec;      // [capR]
+  TLEntry* tl;        // [capL]
+  TileHdr* hdr;       // [ntiles]
+  uint32_t* worklist;    // [ntiles]
+  uint32_t* dense_list;  // [ntiles]
+  u64 capV, capR, capL;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -99,72 +130,106 @@ __host__ __device__ constexpr int edge_b(int e) { return e < 4 ? (e + 1) & 3 : (
 template <bool CO> __host__ __device__ constexpr int corner_df(int n) { return CO ? corner_dz(n) : corner_dx(n); }
 template <bool CO> __host__ __device__ constexpr int corner_dm(int n) { return corner_dy(n); }
 template <bool CO> __host__ __device__ constexpr int corner_ds(int n) { return CO ? corner_dx(n) : corner_dz(n); }
+// corner index at memory offset (+f), (+m), (+s)
+template <bool CO> __host__ __device__ constexpr int corner_plus_f() { return CO ? 3 : 1; }
+template <bool CO> __host__ __device__ constexpr int corner_plus_m() { return 4; }
+template <bool CO> __host__ __device__ constexpr int corner_plus_s() { return CO ? 1 : 3; }
 
-// per edge, 5 bits: owner-voxel offset (of, om, os) and the memory axis of the edge (2 bits).
-// The midpoint M = corner_a + corner_b (half-voxel units): the axis is where M == 1, the owner
-// (lower endpoint) is M >> 1.
+// pass-2 staged own6 region: (TF+1) x (TM+1) x (TS+1) voxels, row pitch RW
+constexpr int RW = 36;
+
+// per edge: bits 0-9 region index delta of the owner voxel, bits 12-14 2*axis, bits 16-18 owner
+// corner, bits 20-22 owner offset (f,m,s).  The midpoint M = corner_a + corner_b (half-voxel
+// units): the axis is where M == 1, the owner (lower endpoint) is M >> 1.
 template <bool CO>
-__host__ __device__ constexpr unsigned long long edge_info_packed() {
-  unsigned long long w = 0;
-  for (int e = 0; e < 12; ++e) {
-    int a = edge_a(e), b = edge_b(e);
-    int mf = corner_df<CO>(a) + corner_df<CO>(b);
-    int mm = corner_dm<CO>(a) + corner_dm<CO>(b);
-    int ms = corner_ds<CO>(a) + corner_ds<CO>(b);
-    int axis = mf == 1 ? 0 : (mm == 1 ? 1 : 2);
-    unsigned long long v = (unsigned long long)((mf >> 1) | ((mm >> 1) << 1) | ((ms >> 1) << 2) | (axis << 3));
-    w |= v << (5 * e);
-  }
-  return w;
+__host__ __device__ constexpr uint32_t edge_info(int e) {
+  int a = edge_a(e), b = edge_b(e);
+  int mf = corner_df<CO>(a) + corner_df<CO>(b);
+  int mm = corner_dm<CO>(a) + corner_dm<CO>(b);
+  int ms = corner_ds<CO>(a) + corner_ds<CO>(b);
+  int axis = mf == 1 ? 0 : (mm == 1 ? 1 : 2);
+  int of = mf >> 1, om = mm >> 1, os = ms >> 1;
+  int oc = 0;
+  for (int n = 0; n < 8; ++n)
+    if (corner_df<CO>(n) == of && corner_dm<CO>(n) == om && corner_ds<CO>(n) == os) oc = n;
+  int delta = (os * RM + om) * RW + of;
+  return (uint32_t)(delta | ((2 * axis) << 12) | (oc << 16) | (of << 20) | (om << 21) | (os << 22));
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA (cp.async.bulk.tensor)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, u64* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
 }
 
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint32_t hash_label(unsigned long long x) {
+__device__ __forceinline__ uint32_t hash_label(u64 x) {
   x ^= x >> 33;
   x *= 0xff51afd7ed558ccdull;
   x ^= x >> 29;
   return (uint32_t)x ^ (uint32_t)(x >> 32);
 }
+__device__ __forceinline__ uint32_t hash_label32(uint32_t x) {
+  x *= 0x9E3779B1u;
+  return x ^ (x >> 15);
+}
+template <typename L> __device__ __forceinline__ uint32_t hash_any(L x) {
+  if (sizeof(L) == 8) return hash_label((u64)x);
+  return hash_label32((uint32_t)x);
+}
 
 // Global table: find-or-insert.  Returns the slot, or -1 (and raises FLAG_HASH_FULL).
-__device__ __forceinline__ int gtab_insert(const LabelTable& ht, unsigned long long label, uint32_t* flags) {
+__device__ __forceinline__ int gtab_insert(const LabelTable& ht, u64 label, uint32_t* flags) {
   uint32_t h = hash_label(label) & ht.mask;
   const uint32_t max_probe = ht.mask < 4095u ? ht.mask + 1u : 4096u;
   for (uint32_t p = 0; p < max_probe; ++p) {
-    unsigned long long old = atomicCAS(&ht.keys[h], 0ull, label);
-    if (old == 0ull || old == label) return (int)h;
+    u64 old = ht.keys[h];
+    if (old == label) return (int)h;
+    if (old == 0ull) {
+      old = atomicCAS(&ht.keys[h], 0ull, label);
+      if (old == 0ull || old == label) return (int)h;
+    }
     h = (h + 1u) & ht.mask;
   }
   atomicOr(flags, FLAG_HASH_FULL);
   return -1;
 }
 
-// Global table: read-only lookup (pass 2; the key must exist).
-__device__ __forceinline__ int gtab_find(const LabelTable& ht, unsigned long long label, uint32_t* flags) {
-  uint32_t h = hash_label(label) & ht.mask;
-  const uint32_t max_probe = ht.mask < 4095u ? ht.mask + 1u : 4096u;
-  for (uint32_t p = 0; p < max_probe; ++p) {
-    unsigned long long k = ht.keys[h];
-    if (k == label) return (int)h;
-    if (k == 0ull) break;
-    h = (h + 1u) & ht.mask;
-  }
-  atomicOr(flags, FLAG_INTERNAL);
-  return -1;
-}
-
-// CTA-local table in shared memory.  A label either gets a slot (all later lookups succeed) or
-// every attempt fails identically (slots are never freed and the probe sequence is a function of
-// the label), in which case callers go to the global table directly.
-__device__ __forceinline__ int ltab_insert(unsigned long long* keys, unsigned long long label) {
-  uint32_t h = hash_label(label) & (LT - 1);
+// CTA-local table in shared memory (keys only; 0 = empty).  Returns the slot or -1 when PROBES
+// probes found neither the label nor a free slot.
+template <int LT, int PROBES>
+__device__ __forceinline__ int ltab_insert(u64* keys, u64 label, uint32_t h) {
+  h &= (LT - 1);
 #pragma unroll 1
-  for (int p = 0; p < LT_PROBES; ++p) {
-    unsigned long long k = *(volatile unsigned long long*)&keys[h];
+  for (int p = 0; p < PROBES; ++p) {
+    u64 k = *(volatile u64*)&keys[h];
     if (k == label) return (int)h;
     if (k == 0ull) {
-      unsigned long long old = atomicCAS(&keys[h], 0ull, label);
+      u64 old = atomicCAS(&keys[h], 0ull, label);
       if (old == 0ull || old == label) return (int)h;
     }
     h = (h + 1u) & (LT - 1);
@@ -172,590 +237,491 @@ __device__ __forceinline__ int ltab_insert(unsigned long long* keys, unsigned lo
   return -1;
 }
 
-__device__ __forceinline__ int ltab_find(const unsigned long long* keys, unsigned long long label) {
-  uint32_t h = hash_label(label) & (LT - 1);
-#pragma unroll 1
-  for (int p = 0; p < LT_PROBES; ++p) {
-    unsigned long long k = keys[h];
-    if (k == label) return (int)h;
-    if (k == 0ull) return -1;
-    h = (h + 1u) & (LT - 1);
-  }
-  return -1;
+// exclusive in-warp prefix and warp total of a per-lane count c in [0, 7], via three ballots
+__device__ __forceinline__ uint32_t warp_prefix3(uint32_t c, uint32_t ltm, uint32_t& total) {
+  const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1u);
+  const uint32_t b1 = __ballot_sync(0xffffffffu, c & 2u);
+  const uint32_t b2 = __ballot_sync(0xffffffffu, c & 4u);
+  total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+  return __popc(b0 & ltm) + 2u * __popc(b1 & ltm) + 4u * __popc(b2 & ltm);
 }
-
-// ---------------------------------------------------------------------------------------------
-// tile staging: region of (TF+H) x (TM+H) x (TS+H) labels, origin = tile origin, zero outside
-// the input volume (this is also what makes `close` free: the virtual border reads as 0).
-
-template <typename L, int H>
-__device__ __forceinline__ void load_region(const VolParams& vp, L* lab, uint32_t ef0, uint32_t em0, uint32_t es0) {
-  constexpr int RF = TF + H, RM = TM + H, RS = TS + H;
-  const L* __restrict__ src = static_cast<const L*>(vp.data);
-  for (int i = threadIdx.x; i < RF * RM * RS; i += NT) {
-    int lf = i % RF;
-    int t = i / RF;
-    int lm = t % RM;
-    int ls = t / RM;
-    uint32_t jf = ef0 + lf - vp.pad, jm = em0 + lm - vp.pad, js = es0 + ls - vp.pad;  // wraps when < 0
-    L v = 0;
-    if (jf < vp.nf && jm < vp.nm && js < vp.ns) v = src[((size_t)js * vp.nm + jm) * vp.nf + jf];
-    lab[i] = v;
-  }
-}
-
-struct TileCoord {
-  uint32_t tf, tm, ts, ef0, em0, es0;
-};
-
-__device__ __forceinline__ TileCoord tile_coord(const VolParams& vp) {
-  TileCoord t;
-  uint32_t b = blockIdx.x;
-  t.tf = b % vp.ntf;
-  b /= vp.ntf;
-  t.tm = b % vp.ntm;
-  t.ts = b / vp.ntm;
-  t.ef0 = t.tf * TF;
-  t.em0 = t.tm * TM;
-  t.es0 = t.ts * TS;
-  return t;
-}
-
-// 6-bit slot mask of voxel (lf,lm,ls) given its label a and its +f,+m,+s neighbours; validity of
-// the voxel and of each neighbour (inside the extended volume) passed in.
-template <typename L>
-__device__ __forceinline__ uint32_t slot_mask(L a, L bf, L bm, L bs, bool vf, bool vm, bool vs) {
-  uint32_t m = 0;
-  if (vf && a != bf) m |= (a != 0 ? 1u : 0u) | (bf != 0 ? 2u : 0u);
-  if (vm && a != bm) m |= (a != 0 ? 4u : 0u) | (bm != 0 ? 8u : 0u);
-  if (vs && a != bs) m |= (a != 0 ? 16u : 0u) | (bs != 0 ? 32u : 0u);
-  return m;
-}
-
-// The cube with origin (lf,lm,ls): 8 corner labels in the reference's corner order.
-template <typename L, bool CO, int RF, int RM>
-__device__ __forceinline__ void load_cube(const L* lab, int lf, int lm, int ls, unsigned long long c[8]) {
-#pragma unroll
-  for (int n = 0; n < 8; ++n)
-    c[n] = (unsigned long long)lab[((ls + corner_ds<CO>(n)) * RM + (lm + corner_dm<CO>(n))) * RF + (lf + corner_df<CO>(n))];
-}
-
-__device__ __forceinline__ bool cube_uniform(const unsigned long long c[8]) {
-  return c[0] == c[1] && c[0] == c[2] && c[0] == c[3] && c[0] == c[4] && c[0] == c[5] && c[0] == c[6] && c[0] == c[7];
+// same, restricted to the lanes of `grp` (a __match_any_sync group containing this lane)
+__device__ __forceinline__ uint32_t group_prefix3(uint32_t c, uint32_t grp, uint32_t ltm, uint32_t& total) {
+  const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1u) & grp;
+  const uint32_t b1 = __ballot_sync(0xffffffffu, c & 2u) & grp;
+  const uint32_t b2 = __ballot_sync(0xffffffffu, c & 4u) & grp;
+  total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+  return __popc(b0 & ltm) + 2u * __popc(b1 & ltm) + 4u * __popc(b2 & ltm);
 }
 
 // ---------------------------------------------------------------------------------------------
 // pass 1: classify + count + reserve
 
-template <typename L>
-__host__ __device__ constexpr size_t classify_smem_bytes() { return sizeof(L) * (TF + 1) * (TM + 1) * (TS + 1); }
-template <typename L>
-__host__ __device__ constexpr size_t emit_smem_bytes() { return sizeof(L) * (TF + 2) * (TM + 2) * (TS + 2); }
+template <typename L, int MODE>
+struct __align__(128) P1Smem {
+  static constexpr int RFP = RowPad<L>::value;
+  L lab[RS * RM * RFP];  // TMA destination: must stay first (128-byte aligned)
+  u64 lkeys[Caps<MODE>::LT];
+  u64 mbar;
+  u64 recbase;
+  uint32_t lcnt[Caps<MODE>::LT];  // low 16: vertices of the label in this tile, high 16: triangles
+  uint32_t lvb[Caps<MODE>::LT];   // first rank of the tile's vertices inside the label
+  uint32_t vstage[Caps<MODE>::VCAP];  // per tile-local slot: local rank << 12 | table slot
+  uint32_t rstage[Caps<MODE>::RCAP];  // voxel-in-tile | case << 11 | table slot << 19
+  uint32_t rowcnt[TM * TS], rowpre[TM * TS];
+  uint32_t nact, nrec, nlab, nslots, overflow, ok, gbase, tlbase, ci, ttot;
+  uint16_t cidx[Caps<MODE>::LT];
+  uint16_t alist[TILE_VOX];
+  uint8_t o6s[TILE_VOX], pre8s[TILE_VOX], tricount[256];
+};
 
-extern __shared__ __align__(16) unsigned char zm_dyn_smem[];
+extern __shared__ __align__(128) unsigned char zm_dyn_smem[];
 
-template <typename L, bool CO>
-__global__ void __launch_bounds__(NT) k_classify(const VolParams vp, const Pass1Args o) {
-  constexpr int RF = TF + 1, RM = TM + 1;
-  L* lab = reinterpret_cast<L*>(zm_dyn_smem);  // [TS+1][TM+1][TF+1]
-  __shared__ unsigned long long lkeys[LT];
-  __shared__ uint32_t lvcnt[LT];  // vertices per local label, then the running rank cursor
-  __shared__ uint32_t ltcnt[LT];
-  __shared__ uint32_t rowcnt[TM * TS];
-  __shared__ uint32_t rowpre[TM * TS];
-  __shared__ unsigned long long s_tilebase;
-  __shared__ uint32_t s_ok;
-  __shared__ uint8_t s_tricount[256];
+template <typename L, bool CO, int MODE>
+__device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtensorMap* tmap, const Pass1Args& o,
+                                              P1Smem<L, MODE>& S, const uint32_t tile, uint32_t& parity) {
+  constexpr int RFP = P1Smem<L, MODE>::RFP;
+  constexpr int LT = Caps<MODE>::LT, VCAP = Caps<MODE>::VCAP, RCAP = Caps<MODE>::RCAP, PROBES = Caps<MODE>::PROBES;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ltm = (1u << lane) - 1u;
 
-  const TileCoord tc = tile_coord(vp);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t b = tile;
+  const uint32_t tf = b % vp.ntf;
+  b /= vp.ntf;
+  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
+  const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
 
-  load_region<L, 1>(vp, lab, tc.ef0, tc.em0, tc.es0);
-  __syncthreads();
-
-  // ---- phase A: slot masks (packed in registers), row counts, activity ----
-  const int ls = warp, lf = lane;
-  const uint32_t ef = tc.ef0 + lf, es = tc.es0 + ls;
-  unsigned long long sm6p = 0;  // byte j: 6-bit slot mask of voxel (lf, j, ls)
-  unsigned long long prep = 0;  // byte j: exclusive in-row prefix of slot counts (<= 186)
-  uint32_t active = 0;          // bit j: cube (lf, j, ls) exists and is non-uniform
-#pragma unroll
-  for (int j = 0; j < TM; ++j) {
-    const int lm = j;
-    const uint32_t em = tc.em0 + lm;
-    const bool valid = ef < vp.Ef && em < vp.Em && es < vp.Es;
-    const int idx = (ls * RM + lm) * RF + lf;
-    const L a = lab[idx], bf = lab[idx + 1], bm = lab[idx + RF], bs = lab[idx + RF * RM];
-    const uint32_t m = valid ? slot_mask<L>(a, bf, bm, bs, ef + 1 < vp.Ef, em + 1 < vp.Em, es + 1 < vp.Es) : 0u;
-    const uint32_t c = __popc(m);
-    uint32_t inc = c;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
+  // ---- S0: stage the label region; clear the tile tables meanwhile ----
+  // TMA needs a 16-byte aligned start along f: with the `close` border the box starts ALIGN
+  // elements (not 1) before the tile and the region sits `coff` columns into the staged rows.
+  constexpr int ALIGN = 16 / (int)sizeof(L);
+  const int coff = vp.pad ? ALIGN - 1 : 0;
+  L* const lab = S.lab + coff;
+  if (vp.use_tma) {
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&S.mbar, (uint32_t)(sizeof(L) * RS * RM * RFP));
+      tma_load_3d(S.lab, tmap, &S.mbar, (int)ef0 - (vp.pad ? ALIGN : 0), (int)em0 - (int)vp.pad, (int)es0 - (int)vp.pad);
     }
-    sm6p |= (unsigned long long)m << (8 * j);
-    prep |= (unsigned long long)(inc - c) << (8 * j);
-    if (lane == 31) rowcnt[ls * TM + lm] = inc;
-    if (valid && ef + 1 < vp.Ef && em + 1 < vp.Em && es + 1 < vp.Es) {
-      unsigned long long cl[8];
-      load_cube<L, CO, RF, RM>(lab, lf, lm, ls, cl);
-      if (!cube_uniform(cl)) active |= 1u << j;
+  } else {
+    const L* __restrict__ src = static_cast<const L*>(vp.data);
+    for (int i = tid; i < (TF + 1) * RM * RS; i += NT) {
+      const int lf = i % (TF + 1);
+      const int t = i / (TF + 1);
+      const int lm = t % RM, ls = t / RM;
+      const uint32_t jf = ef0 + lf - vp.pad, jm = em0 + lm - vp.pad, js = es0 + ls - vp.pad;  // wraps when < 0
+      L v = 0;
+      if (jf < vp.nf && jm < vp.nm && js < vp.ns) v = src[((size_t)js * vp.nm + jm) * vp.nf + jf];
+      lab[(ls * RM + lm) * RFP + lf] = v;
     }
   }
-  if (!__syncthreads_or((sm6p != 0ull || active != 0u) ? 1 : 0)) return;  // uniform tile
-
-  for (int i = threadIdx.x; i < LT; i += NT) { lkeys[i] = 0ull; lvcnt[i] = 0u; ltcnt[i] = 0u; }
-  s_tricount[threadIdx.x] = TRI_COUNT_D[threadIdx.x];
-  __syncthreads();
-
-  // ---- phase B: per-(tile,label) counts in the local table ----
-#pragma unroll 1
-  for (int j = 0; j < TM; ++j) {
-    const int lm = j;
-    const int idx = (ls * RM + lm) * RF + lf;
-    const uint32_t m = (uint32_t)(sm6p >> (8 * j)) & 63u;
-    if (m) {
-      const L a = lab[idx];
-      const uint32_t na = __popc(m & 0x15u);  // slots carrying my own label
-      if (na) {
-        int s = ltab_insert(lkeys, (unsigned long long)a);
-        if (s >= 0) atomicAdd(&lvcnt[s], na);
-      }
-#pragma unroll
-      for (int d = 0; d < 3; ++d)
-        if (m & (2u << (2 * d))) {
-          const L b = lab[idx + (d == 0 ? 1 : (d == 1 ? RF : RF * RM))];
-          int s = ltab_insert(lkeys, (unsigned long long)b);
-          if (s >= 0) atomicAdd(&lvcnt[s], 1u);
-        }
-    }
-    if (active & (1u << j)) {
-      unsigned long long cl[8];
-      load_cube<L, CO, RF, RM>(lab, lf, lm, ls, cl);
-      uint32_t acc = 0;
-      while (acc != 0xFFu) {
-        const int start = __ffs(~acc & 0xFFu) - 1;
-        unsigned long long label = cl[0];
-#pragma unroll
-        for (int n = 1; n < 8; ++n) label = (n == start) ? cl[n] : label;
-        uint32_t msk = 0;
-#pragma unroll
-        for (int n = 0; n < 8; ++n) msk |= (cl[n] == label ? 1u : 0u) << n;
-        acc |= msk;
-        if (label == 0ull) continue;
-        const uint32_t nt = s_tricount[~msk & 0xFFu];
-        if (nt == 0u) continue;
-        int s = ltab_insert(lkeys, label);
-        if (s >= 0) atomicAdd(&ltcnt[s], nt);
-        else {
-          int gs = gtab_insert(o.ht, label, o.flags);
-          if (gs >= 0) atomicAdd(&o.ht.cntT[gs], nt);
-        }
-      }
-    }
+  for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
+  if (tid == 0) { S.nact = 0; S.nrec = 0; S.nlab = 0; S.overflow = 0; S.ci = 0; S.ttot = 0; }
+  if (vp.use_tma) {
+    mbar_wait(&S.mbar, parity);
+    parity ^= 1u;
   }
   __syncthreads();
 
-  // ---- phase C: reserve per-label rank ranges and the tile's perm segment ----
-  for (int i = threadIdx.x; i < LT; i += NT) {
-    const unsigned long long label = lkeys[i];
-    if (label != 0ull) {
-      const uint32_t nv = lvcnt[i], nt = ltcnt[i];
-      const int gs = gtab_insert(o.ht, label, o.flags);
-      uint32_t base = 0;
-      if (gs >= 0) {
-        if (nv) {
-          base = atomicAdd(&o.ht.cntV[gs], nv);
-          if (base + nv < base) atomicOr(o.flags, FLAG_RANK_OVERFLOW);
-        }
-        if (nt) atomicAdd(&o.ht.cntT[gs], nt);
+  // ---- S1: slot masks, in-row prefixes, compaction of active voxels ----
+  {
+    const int ls = warp;
+    const uint32_t ef = ef0 + lane, es = es0 + ls;
+    const bool okf = ef < vp.Ef, oks = es < vp.Es, nf1 = ef + 1 < vp.Ef, ns1 = es + 1 < vp.Es;
+    const int i0 = (ls * RM) * RFP + lane;
+    L a = lab[i0], af = lab[i0 + 1], as_ = lab[i0 + RM * RFP], afs = lab[i0 + RM * RFP + 1];
+#pragma unroll
+    for (int j = 0; j < TM; ++j) {
+      const int in = (ls * RM + j + 1) * RFP + lane;
+      const L am = lab[in], afm = lab[in + 1], ams = lab[in + RM * RFP], afms = lab[in + RM * RFP + 1];
+      const uint32_t em = em0 + j;
+      const bool okm = em < vp.Em, nm1 = em + 1 < vp.Em;
+      const bool valid = okf && okm && oks;
+      uint32_t m = 0;
+      if (valid) {
+        if (nf1 && a != af) m |= (a != 0 ? 1u : 0u) | (af != 0 ? 2u : 0u);
+        if (nm1 && a != am) m |= (a != 0 ? 4u : 0u) | (am != 0 ? 8u : 0u);
+        if (ns1 && a != as_) m |= (a != 0 ? 16u : 0u) | (as_ != 0 ? 32u : 0u);
       }
-      lvcnt[i] = base;
+      const bool cube = valid && nf1 && nm1 && ns1;
+      const bool uniform = a == af && a == am && a == as_ && a == afm && a == afs && a == ams && a == afms;
+      const bool act = (m != 0u) || (cube && !uniform);
+      if (okm && oks) o.own6[((size_t)es * vp.Em + em) * vp.Efp + ef] = (uint8_t)m;
+      const int vidx = (ls * TM + j) * TF + lane;
+      uint32_t rowtotal = 0;
+      if (__ballot_sync(FULL, m != 0u)) {
+        const uint32_t pre = warp_prefix3(__popc(m), ltm, rowtotal);
+        S.o6s[vidx] = (uint8_t)m;
+        S.pre8s[vidx] = (uint8_t)pre;
+      } else if (act) {
+        S.o6s[vidx] = 0;
+      }
+      if (lane == 0) S.rowcnt[ls * TM + j] = rowtotal;
+      const uint32_t ab = __ballot_sync(FULL, act);
+      if (ab) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&S.nact, (uint32_t)__popc(ab));
+        base = __shfl_sync(FULL, base, 0);
+        if (act) S.alist[base + __popc(ab & ltm)] = (uint16_t)vidx;
+      }
+      a = am; af = afm; as_ = ams; afs = afms;
     }
   }
+  __syncthreads();
+
+  // ---- S2: row bases inside the tile ----
   if (warp == 0) {
-    const uint32_t a0 = rowcnt[2 * lane], a1 = rowcnt[2 * lane + 1];
+    const uint32_t a0 = S.rowcnt[2 * lane], a1 = S.rowcnt[2 * lane + 1];
     const uint32_t sum = a0 + a1;
     uint32_t inc = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      uint32_t t = __shfl_up_sync(FULL, inc, d);
       if (lane >= d) inc += t;
     }
-    rowpre[2 * lane] = inc - sum;
-    rowpre[2 * lane + 1] = inc - sum + a0;
-    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-    if (lane == 0) {
-      const unsigned long long base = total ? atomicAdd(o.cursor, (unsigned long long)total) : 0ull;
-      const bool ok = base + total <= o.permcap;
-      if (!ok) atomicOr(o.flags, FLAG_PERM_FULL);
-      s_tilebase = base;
-      s_ok = ok ? 1u : 0u;
-    }
+    S.rowpre[2 * lane] = inc - sum;
+    S.rowpre[2 * lane + 1] = inc - sum + a0;
+    if (lane == 31) S.nslots = inc;
   }
   __syncthreads();
-  if (!s_ok) return;  // capacity guess too small: the cursor still gives the exact need; host reruns
-  const unsigned long long tilebase = s_tilebase;
-
-  // rowbase for the rows of this tile (row id = (es*Em + em)*ntf + tf)
-  if (threadIdx.x < TM * TS) {
-    const int r = threadIdx.x;
-    const uint32_t rs = tc.es0 + r / TM, rm = tc.em0 + r % TM;
-    if (rs < vp.Es && rm < vp.Em)
-      o.rowbase[((size_t)rs * vp.Em + rm) * vp.ntf + tc.tf] = (uint32_t)(tilebase + rowpre[r]);
+  const uint32_t nslots = S.nslots, nact = S.nact;
+  if (nslots == 0u && nact == 0u) return;  // uniform tile: nothing but the own6 zeros
+  if (MODE == 0 && nslots > (uint32_t)VCAP) {
+    if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
+    return;
   }
 
-  // ---- phase D: vertex ranks -> perm[g] ----
-#pragma unroll 1
-  for (int j = 0; j < TM; ++j) {
-    const uint32_t m = (uint32_t)(sm6p >> (8 * j)) & 63u;
-    if (!m) continue;
-    const int lm = j;
-    const int idx = (ls * RM + lm) * RF + lf;
-    const L a = lab[idx];
-    unsigned long long g = tilebase + rowpre[ls * TM + lm] + ((uint32_t)(prep >> (8 * j)) & 255u);
+  // ---- S3: per active voxel: distinct labels of its cube -> counts, local ranks, records ----
+  for (uint32_t base = warp * 32; base < nact; base += NT) {
+    const uint32_t i = base + lane;
+    const bool valid = i < nact;
+    const uint32_t vidx = valid ? S.alist[i] : 0u;
+    const int lf = vidx & 31, lm = (vidx >> 5) & 7, ls = vidx >> 8;
+    L c[8];
 #pragma unroll
-    for (int s6 = 0; s6 < 6; ++s6) {
-      if (!(m & (1u << s6))) continue;
-      const int d = s6 >> 1;
-      const unsigned long long label =
-          (s6 & 1) ? (unsigned long long)lab[idx + (d == 0 ? 1 : (d == 1 ? RF : RF * RM))] : (unsigned long long)a;
-      const int s = ltab_find(lkeys, label);
-      uint32_t rank;
-      if (s >= 0) rank = atomicAdd(&lvcnt[s], 1u);
-      else {
-        const int gs = gtab_insert(o.ht, label, o.flags);
-        rank = gs >= 0 ? atomicAdd(&o.ht.cntV[gs], 1u) : 0u;
-      }
-      o.perm[g] = rank;
-      ++g;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// pass 2: emit vertex keys and faces
-
-template <typename L, bool CO>
-__global__ void __launch_bounds__(NT) k_emit(const VolParams vp, const Pass2Args o) {
-  constexpr int RF = TF + 2, RM = TM + 2;               // labels: halo 2
-  constexpr int AF = TF + 1, AM = TM + 1, AS = TS + 1;  // voxels whose slots can be referenced
-  L* lab = reinterpret_cast<L*>(zm_dyn_smem);           // [TS+2][TM+2][TF+2]
-  __shared__ uint8_t own6[AF * AM * AS];
-  __shared__ uint8_t pre8[AF * AM * AS];
-  __shared__ uint32_t rb[AM * AS][2];  // rowbase of the row in this tile column / in the next one
-  __shared__ unsigned long long lkeys[LT];
-  __shared__ uint32_t ltcnt[LT];  // triangles per local label, then the running cursor
-  __shared__ uint32_t lgs[LT];    // global slot of the local label
-  __shared__ unsigned long long s_trinib[256];
-  __shared__ uint8_t s_tricount[256];
-
-  const TileCoord tc = tile_coord(vp);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-  load_region<L, 2>(vp, lab, tc.ef0, tc.em0, tc.es0);
-  __syncthreads();
-
-  // ---- phase A: slot masks + in-row prefixes for the (TF+1)(TM+1)(TS+1) referenced voxels ----
-  bool any = false;
-  for (int r = warp; r < AM * AS; r += NW) {
-    const int lm = r % AM, ls = r / AM;
-    const uint32_t em = tc.em0 + lm, es = tc.es0 + ls;
-    const bool rowvalid = em < vp.Em && es < vp.Es;
-    {
-      const int lf = lane;
-      const uint32_t ef = tc.ef0 + lf;
-      const int idx = (ls * RM + lm) * RF + lf;
-      uint32_t m = 0;
-      if (rowvalid && ef < vp.Ef)
-        m = slot_mask<L>(lab[idx], lab[idx + 1], lab[idx + RF], lab[idx + RF * RM], ef + 1 < vp.Ef,
-                         em + 1 < vp.Em, es + 1 < vp.Es);
-      const uint32_t c = __popc(m);
-      uint32_t inc = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-      }
-      own6[(ls * AM + lm) * AF + lf] = (uint8_t)m;
-      pre8[(ls * AM + lm) * AF + lf] = (uint8_t)(inc - c);
-      any |= (m != 0u);
-    }
-    if (lane == 0) {  // halo column lf == TF: first voxel of the next tile's row
-      const int lf = TF;
-      const uint32_t ef = tc.ef0 + lf;
-      const int idx = (ls * RM + lm) * RF + lf;
-      uint32_t m = 0;
-      if (rowvalid && ef < vp.Ef)
-        m = slot_mask<L>(lab[idx], lab[idx + 1], lab[idx + RF], lab[idx + RF * RM], ef + 1 < vp.Ef,
-                         em + 1 < vp.Em, es + 1 < vp.Es);
-      own6[(ls * AM + lm) * AF + lf] = (uint8_t)m;
-      pre8[(ls * AM + lm) * AF + lf] = 0;
-      any |= (m != 0u);
-      const size_t row = ((size_t)es * vp.Em + em) * vp.ntf + tc.tf;
-      rb[r][0] = rowvalid ? o.rowbase[row] : 0u;
-      rb[r][1] = (rowvalid && tc.tf + 1 < vp.ntf) ? o.rowbase[row + 1] : 0u;
-    }
-  }
-  // every edge of an owned cube, and every owned edge, is owned by one of the voxels above
-  if (!__syncthreads_or(any ? 1 : 0)) return;
-
-  for (int i = threadIdx.x; i < LT; i += NT) { lkeys[i] = 0ull; ltcnt[i] = 0u; }
-  s_tricount[threadIdx.x] = TRI_COUNT_D[threadIdx.x];
-  s_trinib[threadIdx.x] = TRI_NIBBLES_D[threadIdx.x];
-  __syncthreads();
-
-  // ---- phase B: triangles per (tile,label) ----
-  const int ls = warp, lf = lane;
-  const uint32_t ef = tc.ef0 + lf, es = tc.es0 + ls;
-  uint32_t active = 0;
-#pragma unroll 1
-  for (int j = 0; j < TM; ++j) {
-    const int lm = j;
-    const uint32_t em = tc.em0 + lm;
-    if (!(ef + 1 < vp.Ef && em + 1 < vp.Em && es + 1 < vp.Es)) continue;
-    unsigned long long cl[8];
-    load_cube<L, CO, RF, RM>(lab, lf, lm, ls, cl);
-    if (cube_uniform(cl)) continue;
-    active |= 1u << j;
-    uint32_t acc = 0;
-    while (acc != 0xFFu) {
+    for (int n = 0; n < 8; ++n)
+      c[n] = lab[((ls + corner_ds<CO>(n)) * RM + (lm + corner_dm<CO>(n))) * RFP + (lf + corner_df<CO>(n))];
+    const uint32_t m = valid ? S.o6s[vidx] : 0u;
+    const bool cube = (ef0 + lf + 1 < vp.Ef) && (em0 + lm + 1 < vp.Em) && (es0 + ls + 1 < vp.Es);
+    const uint32_t gl0 = m ? S.rowpre[ls * TM + lm] + S.pre8s[vidx] : 0u;
+    uint32_t acc = valid ? 0u : 0xFFu;
+    while (__any_sync(FULL, acc != 0xFFu)) {
+      const bool have = acc != 0xFFu;
       const int start = __ffs(~acc & 0xFFu) - 1;
-      unsigned long long label = cl[0];
+      L label = c[0];
 #pragma unroll
-      for (int n = 1; n < 8; ++n) label = (n == start) ? cl[n] : label;
+      for (int n = 1; n < 8; ++n) label = (n == start) ? c[n] : label;
       uint32_t msk = 0;
 #pragma unroll
-      for (int n = 0; n < 8; ++n) msk |= (cl[n] == label ? 1u : 0u) << n;
-      acc |= msk;
-      if (label == 0ull) continue;
-      const uint32_t nt = s_tricount[~msk & 0xFFu];
-      if (nt == 0u) continue;
-      int s = ltab_insert(lkeys, label);
-      if (s >= 0) atomicAdd(&ltcnt[s], nt);
-    }
-  }
-  __syncthreads();
-
-  // ---- phase C: reserve the tile's face ranges ----
-  for (int i = threadIdx.x; i < LT; i += NT) {
-    const unsigned long long label = lkeys[i];
-    if (label != 0ull) {
-      const int gs = gtab_find(o.ht, label, o.flags);
-      const uint32_t nt = ltcnt[i];
-      const uint32_t base = (gs >= 0 && nt) ? atomicAdd(&o.curT[gs], nt) : 0u;
-      ltcnt[i] = base;
-      lgs[i] = gs >= 0 ? (uint32_t)gs : 0xFFFFFFFFu;
-    }
-  }
-  __syncthreads();
-
-  // ---- phase D: owned vertices -> keys at their final position ----
-#pragma unroll 1
-  for (int j = 0; j < TM; ++j) {
-    const int lm = j;
-    const int aidx = (ls * AM + lm) * AF + lf;
-    const uint32_t m = own6[aidx];
-    if (!m) continue;
-    const uint32_t em = tc.em0 + lm;
-    const int idx = (ls * RM + lm) * RF + lf;
-    const L a = lab[idx];
-    uint32_t g = rb[ls * AM + lm][0] + pre8[aidx];
-#pragma unroll
-    for (int s6 = 0; s6 < 6; ++s6) {
-      if (!(m & (1u << s6))) continue;
-      const int d = s6 >> 1;
-      const unsigned long long label =
-          (s6 & 1) ? (unsigned long long)lab[idx + (d == 0 ? 1 : (d == 1 ? RF : RF * RM))] : (unsigned long long)a;
-      const int s = ltab_find(lkeys, label);
-      const int gs = s >= 0 ? (int)lgs[s] : gtab_find(o.ht, label, o.flags);
-      const uint32_t rank = o.perm[g];
-      ++g;
-      if (gs < 0) continue;
-      // half-voxel coordinates of the edge midpoint, memory axes -> logical axes
-      const unsigned long long hf = 2ull * ef + (d == 0), hm = 2ull * em + (d == 1), hs = 2ull * es + (d == 2);
-      const unsigned long long kx = (CO ? hs : hf) + 2ull * vp.ox;
-      const unsigned long long ky = hm + 2ull * vp.oy;
-      const unsigned long long kz = (CO ? hf : hs) + 2ull * vp.oz;
-      o.vkeys[o.offV[gs] + rank] = (kx << 42) | (ky << 21) | kz;
-    }
-  }
-
-  // ---- phase E: faces ----
-  constexpr unsigned long long EINFO = edge_info_packed<CO>();
-#pragma unroll 1
-  for (int j = 0; j < TM; ++j) {
-    if (!(active & (1u << j))) continue;
-    const int lm = j;
-    unsigned long long cl[8];
-    load_cube<L, CO, RF, RM>(lab, lf, lm, ls, cl);
-    uint32_t acc = 0;
-    while (acc != 0xFFu) {
-      const int start = __ffs(~acc & 0xFFu) - 1;
-      unsigned long long label = cl[0];
-#pragma unroll
-      for (int n = 1; n < 8; ++n) label = (n == start) ? cl[n] : label;
-      uint32_t msk = 0;
-#pragma unroll
-      for (int n = 0; n < 8; ++n) msk |= (cl[n] == label ? 1u : 0u) << n;
-      acc |= msk;
-      if (label == 0ull) continue;
+      for (int n = 0; n < 8; ++n) msk |= (c[n] == label ? 1u : 0u) << n;
+      if (have) acc |= msk;
       const uint32_t cs = ~msk & 0xFFu;
-      const uint32_t nt = s_tricount[cs];
-      if (nt == 0u) continue;
-      const int s = ltab_find(lkeys, label);
-      int gs;
-      uint32_t tb;
-      if (s >= 0) {
-        gs = (int)lgs[s];
-        tb = atomicAdd(&ltcnt[s], nt);
-      } else {
-        gs = gtab_find(o.ht, label, o.flags);
-        tb = gs >= 0 ? atomicAdd(&o.curT[gs], nt) : 0u;
+      uint32_t nt = 0, mine = 0;
+      if (have && label != 0) {
+        if (cube) nt = S.tricount[cs];
+        mine = (((msk >> 0) & 1u) * 0x15u) | (((msk >> corner_plus_f<CO>()) & 1u) << 1) |
+               (((msk >> corner_plus_m<CO>()) & 1u) << 3) | (((msk >> corner_plus_s<CO>()) & 1u) << 5);
+        mine &= m;
       }
-      if (gs < 0) continue;
-      uint32_t* fout = o.faces + 3ull * (o.offT[gs] + tb);
-      const unsigned long long nib = s_trinib[cs];
-      for (uint32_t t = 0; t < nt; ++t) {
-        uint32_t vidx[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int e = (int)((nib >> (12 * t + 4 * k)) & 0xFull);
-          const uint32_t info = (uint32_t)(EINFO >> (5 * e)) & 31u;
-          const int uf = lf + (int)(info & 1u), um = lm + (int)((info >> 1) & 1u), us = ls + (int)((info >> 2) & 1u);
-          const uint32_t d = info >> 3;
-          // side 0: the owner (lower) voxel carries `label`; side 1: the upper one does
-          const unsigned long long lower = (unsigned long long)lab[(us * RM + um) * RF + uf];
-          const uint32_t slot = 2u * d + (lower == label ? 0u : 1u);
-          const int aidx = (us * AM + um) * AF + uf;
-          const uint32_t g = rb[us * AM + um][uf == TF ? 1 : 0] + pre8[aidx] +
-                             __popc((uint32_t)own6[aidx] & ((1u << slot) - 1u));
-          vidx[k] = o.perm[g];
+      const uint32_t nv = __popc(mine);
+      bool work = (nv | nt) != 0u;
+      int hs = -1;
+      if (work) {
+        hs = ltab_insert<LT, PROBES>(S.lkeys, (u64)label, hash_any<L>(label));
+        if (hs < 0) { S.overflow = 1u; work = false; }
+      }
+      // warp-aggregated add of (nv | nt << 16) to lcnt[hs]; the return value ranks the vertices
+      const uint32_t grp = __match_any_sync(FULL, work ? (uint32_t)hs : 0xFFFFFFFFu);
+      const uint32_t glt = grp & ltm;
+      uint32_t totv, tott;
+      const uint32_t prev = group_prefix3(work ? nv : 0u, grp, glt, totv);
+      (void)group_prefix3(work ? nt : 0u, grp, glt, tott);
+      const int leader = __ffs(grp) - 1;
+      uint32_t old = 0;
+      if (work && lane == leader) old = atomicAdd(&S.lcnt[hs], totv | (tott << 16));
+      old = __shfl_sync(FULL, old, leader);
+      if (work && nv) {
+        uint32_t r = (old & 0xFFFFu) + prev;
+        uint32_t mm = mine;
+        while (mm) {
+          const int s6 = __ffs(mm) - 1;
+          mm &= mm - 1u;
+          const uint32_t lg = gl0 + __popc(m & ((1u << s6) - 1u));
+          S.vstage[lg] = (r << 12) | (uint32_t)hs;
+          ++r;
         }
-        // reference winding of Mesher.get: (E[T[3n+1]], E[T[3n]], E[T[3n+2]])
-        // (marching_cubes.hpp:338-343 then cMesher.hpp:158-162)
-        fout[3 * t + 0] = vidx[1];
-        fout[3 * t + 1] = vidx[0];
-        fout[3 * t + 2] = vidx[2];
       }
+      const bool hasrec = work && nt != 0u;
+      const uint32_t rb = __ballot_sync(FULL, hasrec);
+      if (rb) {
+        uint32_t rbase = 0;
+        if (lane == 0) rbase = atomicAdd(&S.nrec, (uint32_t)__popc(rb));
+        rbase = __shfl_sync(FULL, rbase, 0);
+        if (hasrec) {
+          const uint32_t pos = rbase + __popc(rb & ltm);
+          if (pos < (uint32_t)RCAP) S.rstage[pos] = vidx | (cs << 11) | ((uint32_t)hs << 19);
+          else S.overflow = 1u;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (MODE == 0 && S.overflow) {
+    if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
+    return;
+  }
+  if (MODE == 1 && S.overflow) {
+    if (tid == 0) atomicOr(&o.ctl->flags, FLAG_INTERNAL);
+    return;
+  }
+
+  // ---- S5: reserve the tile's segments and the per-label ranges ----
+  {
+    uint32_t nl = 0;
+    for (int i = tid; i < LT; i += NT) nl += (S.lkeys[i] != 0ull) ? 1u : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) nl += __shfl_xor_sync(FULL, nl, d);
+    if (lane == 0 && nl) atomicAdd(&S.nlab, nl);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t nrec = S.nrec, nlab = S.nlab;
+    const u64 gbase = nslots ? atomicAdd(&o.ctl->cur_perm, (u64)nslots) : 0ull;
+    const u64 recbase = nrec ? atomicAdd(&o.ctl->cur_rec, (u64)nrec) : 0ull;
+    const u64 tlbase = nlab ? atomicAdd(&o.ctl->cur_tl, (u64)nlab) : 0ull;
+    const bool ok = gbase + nslots <= o.capV && recbase + nrec <= o.capR && tlbase + nlab <= o.capL;
+    if (!ok) atomicOr(&o.ctl->flags, FLAG_CAP);
+    else {
+      o.worklist[atomicAdd(&o.ctl->work_count, 1u)] = tile;
+      TileHdr h;
+      h.recbase = recbase;
+      h.gbase = (uint32_t)gbase;
+      h.tlbase = (uint32_t)tlbase;
+      h.nslots = (uint16_t)nslots;
+      h.nrec = (uint16_t)nrec;
+      h.nlab = (uint16_t)nlab;
+      h.pad = 0;
+      o.hdr[tile] = h;
+    }
+    S.gbase = (uint32_t)gbase;
+    S.recbase = recbase;
+    S.tlbase = (uint32_t)tlbase;
+    S.ok = ok ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!S.ok) return;  // capacity guess too small: the cursors still give the exact need; host reruns
+  const uint32_t gbase = S.gbase, tlbase = S.tlbase;
+  const u64 recbase = S.recbase;
+  for (int i = tid; i < LT; i += NT) {
+    const u64 label = S.lkeys[i];
+    if (label != 0ull) {
+      const uint32_t cnt = S.lcnt[i];
+      const uint32_t nv = cnt & 0xFFFFu, nt = cnt >> 16;
+      const int gs = gtab_insert(o.ht, label, &o.ctl->flags);
+      u64 old = 0;
+      if (gs >= 0) old = atomicAdd(&o.ht.cnt[gs], (u64)nv | ((u64)nt << 32));
+      const uint32_t ci = atomicAdd(&S.ci, 1u);
+      S.lvb[i] = (uint32_t)old;
+      S.cidx[i] = (uint16_t)ci;
+      TLEntry e;
+      e.a = (u64)(uint32_t)(gs >= 0 ? gs : 0) | (old & 0xFFFFFFFF00000000ull);
+      e.b = 0;
+      o.tl[tlbase + ci] = e;
+      if (nt) atomicAdd(&S.ttot, nt);
+    }
+  }
+  __syncthreads();
+
+  // ---- S6: flush rowbase, perm/vl and the records (coalesced) ----
+  if (tid == 0 && S.ttot) atomicAdd(&o.ctl->cur_tri, (u64)S.ttot);
+  if (tid < TM * TS) {
+    const uint32_t rs = es0 + tid / TM, rm = em0 + tid % TM;
+    if (rs < vp.Es && rm < vp.Em) o.rowbase[((size_t)rs * vp.Em + rm) * vp.ntf + tf] = gbase + S.rowpre[tid];
+  }
+  for (uint32_t i = tid; i < nslots; i += NT) {
+    const uint32_t w = S.vstage[i];
+    const uint32_t hs = w & 0xFFFu;
+    o.perm[(size_t)gbase + i] = S.lvb[hs] + (w >> 12);
+    o.vl[(size_t)gbase + i] = S.cidx[hs];
+  }
+  const uint32_t nrec = S.nrec;
+  for (uint32_t i = tid; i < nrec; i += NT) {
+    const uint32_t w = S.rstage[i];
+    o.rec[recbase + i] = (w & 0x7FFFFu) | ((uint32_t)S.cidx[w >> 19] << 19);
+  }
+}
+
+template <typename L, bool CO, int MODE>
+__global__ void __launch_bounds__(NT) k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap,
+                                                 const Pass1Args o) {
+  P1Smem<L, MODE>& S = *reinterpret_cast<P1Smem<L, MODE>*>(zm_dyn_smem);
+  if (threadIdx.x == 0) {
+    mbar_init(&S.mbar, 1);
+    fence_mbar_init();
+  }
+  S.tricount[threadIdx.x] = TRI_COUNT_D[threadIdx.x];
+  __syncthreads();
+  uint32_t parity = 0;
+  if (MODE == 0) {
+    classify_tile<L, CO, MODE>(vp, &tmap, o, S, blockIdx.x, parity);
+  } else {
+    const uint32_t n = o.ctl->dense_count;  // written by the MODE 0 launch that precedes this one
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+      classify_tile<L, CO, MODE>(vp, &tmap, o, S, o.dense_list[i], parity);
+      __syncthreads();
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// label table scan: per-slot exclusive offsets + compact list of live labels (one CTA)
+// label table scan: per-slot exclusive offsets + compact list of live labels
 
-struct ScanOut {
-  unsigned long long* offV;  // [cap]
-  unsigned long long* offT;  // [cap]
-  unsigned long long* list;  // [cap][3]: label, nV, nT  (compact, table order)
-  unsigned long long* totals;  // [4]: n_labels, V_total, T_total, perm cursor (copied)
+struct ScanArgs {
+  LabelTable ht;
+  u64* offV;     // [cap]
+  u64* offT;     // [cap]
+  u64* list;     // [cap][3]: label, nV, nT  (compact, table order)
+  u64* partial;  // [3][1024]
+  Control* ctl;
+  uint32_t chunk;  // table slots per CTA (multiple of 1024)
 };
 
-__global__ void __launch_bounds__(1024) k_label_scan(const LabelTable ht, const ScanOut so,
-                                                    const unsigned long long* cursor) {
-  __shared__ unsigned long long sV[1024], sT[1024];
-  __shared__ uint32_t sN[1024];
-  const uint32_t cap = ht.mask + 1u;
-  const uint32_t per = (cap + 1023u) / 1024u;
-  const uint32_t lo = threadIdx.x * per, hi = min(cap, lo + per);
-  unsigned long long v = 0, t = 0;
-  uint32_t n = 0;
-  for (uint32_t i = lo; i < hi; ++i) {
-    if (ht.keys[i] != 0ull) {
-      v += ht.cntV[i];
-      t += ht.cntT[i];
-      n += (ht.cntT[i] != 0u || ht.cntV[i] != 0u) ? 1u : 0u;
-    }
+struct Scan3 { u64 v, t; uint32_t n; };
+
+__device__ __forceinline__ Scan3 block_scan3(Scan3 x, Scan3& total, Scan3* sh /*[32]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Scan3 inc = x;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 tv = __shfl_up_sync(0xffffffffu, inc.v, d), tt = __shfl_up_sync(0xffffffffu, inc.t, d);
+    const uint32_t tn = __shfl_up_sync(0xffffffffu, inc.n, d);
+    if (lane >= d) { inc.v += tv; inc.t += tt; inc.n += tn; }
   }
-  sV[threadIdx.x] = v; sT[threadIdx.x] = t; sN[threadIdx.x] = n;
+  if (lane == 31) sh[warp] = inc;
   __syncthreads();
-  // Hillis-Steele inclusive scan over 1024 partials
-  for (int d = 1; d < 1024; d <<= 1) {
-    unsigned long long av = 0, at = 0;
-    uint32_t an = 0;
-    if ((int)threadIdx.x >= d) { av = sV[threadIdx.x - d]; at = sT[threadIdx.x - d]; an = sN[threadIdx.x - d]; }
-    __syncthreads();
-    sV[threadIdx.x] += av; sT[threadIdx.x] += at; sN[threadIdx.x] += an;
-    __syncthreads();
+  if (warp == 0) {
+    Scan3 w = sh[lane];
+    Scan3 wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u64 tv = __shfl_up_sync(0xffffffffu, wi.v, d), tt = __shfl_up_sync(0xffffffffu, wi.t, d);
+      const uint32_t tn = __shfl_up_sync(0xffffffffu, wi.n, d);
+      if (lane >= d) { wi.v += tv; wi.t += tt; wi.n += tn; }
+    }
+    Scan3 ex;
+    ex.v = wi.v - w.v; ex.t = wi.t - w.t; ex.n = wi.n - w.n;
+    sh[lane] = ex;
+    if (lane == 31) sh[32] = wi;
   }
-  unsigned long long bv = sV[threadIdx.x] - v, bt = sT[threadIdx.x] - t;
-  uint32_t bn = sN[threadIdx.x] - n;
-  for (uint32_t i = lo; i < hi; ++i) {
-    so.offV[i] = bv;
-    so.offT[i] = bt;
-    if (ht.keys[i] != 0ull) {
-      uint32_t cv = ht.cntV[i], ct = ht.cntT[i];
-      if (cv != 0u || ct != 0u) {
-        so.list[3ull * bn + 0] = ht.keys[i];
-        so.list[3ull * bn + 1] = cv;
-        so.list[3ull * bn + 2] = ct;
-        ++bn;
-      }
-      bv += cv;
-      bt += ct;
+  __syncthreads();
+  const Scan3 wb = sh[warp];
+  total = sh[32];
+  Scan3 r;
+  r.v = wb.v + inc.v - x.v; r.t = wb.t + inc.t - x.t; r.n = wb.n + inc.n - x.n;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_partials(const ScanArgs a) {
+  __shared__ Scan3 sh[33];
+  const uint32_t lo = blockIdx.x * a.chunk;
+  Scan3 x;
+  x.v = 0; x.t = 0; x.n = 0;
+  for (uint32_t i = lo + threadIdx.x; i < lo + a.chunk; i += 1024) {
+    if (a.ht.keys[i] != 0ull) {
+      const u64 c = a.ht.cnt[i];
+      x.v += c & 0xFFFFFFFFull;
+      x.t += c >> 32;
+      x.n += c != 0ull ? 1u : 0u;
     }
   }
-  if (threadIdx.x == 1023) {
-    so.totals[0] = sN[1023];
-    so.totals[1] = sV[1023];
-    so.totals[2] = sT[1023];
-    so.totals[3] = *cursor;
+  Scan3 total;
+  (void)block_scan3(x, total, sh);
+  if (threadIdx.x == 0) {
+    a.partial[blockIdx.x] = total.v;
+    a.partial[1024 + blockIdx.x] = total.t;
+    a.partial[2048 + blockIdx.x] = total.n;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_apply(const ScanArgs a) {
+  __shared__ Scan3 sh[33];
+  __shared__ Scan3 s_base;
+  Scan3 p;
+  p.v = 0; p.t = 0; p.n = 0;
+  if (threadIdx.x < gridDim.x) {
+    p.v = a.partial[threadIdx.x];
+    p.t = a.partial[1024 + threadIdx.x];
+    p.n = (uint32_t)a.partial[2048 + threadIdx.x];
+  }
+  Scan3 total;
+  const Scan3 ex = block_scan3(p, total, sh);
+  if (threadIdx.x == blockIdx.x) s_base = ex;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    a.ctl->totals[0] = total.n;
+    a.ctl->totals[1] = total.v;
+    a.ctl->totals[2] = total.t;
+    a.ctl->totals[3] = 0;
+  }
+  __syncthreads();
+  Scan3 base = s_base;
+  const uint32_t lo = blockIdx.x * a.chunk;
+  for (uint32_t off = 0; off < a.chunk; off += 1024) {
+    const uint32_t i = lo + off + threadIdx.x;
+    const u64 key = a.ht.keys[i];
+    const u64 c = key != 0ull ? a.ht.cnt[i] : 0ull;
+    Scan3 x;
+    x.v = c & 0xFFFFFFFFull; x.t = c >> 32; x.n = c != 0ull ? 1u : 0u;
+    Scan3 tot;
+    const Scan3 e = block_scan3(x, tot, sh);
+    a.offV[i] = base.v + e.v;
+    a.offT[i] = base.t + e.t;
+    if (x.n) {
+      const u64 li = (u64)base.n + e.n;
+      a.list[3 * li + 0] = key;
+      a.list[3 * li + 1] = x.v;
+      a.list[3 * li + 2] = x.t;
+    }
+    base.v += tot.v; base.t += tot.t; base.n += tot.n;
+  }
+}
+
+// tl[i]: (label slot | face base in label << 32)  ->  (first vertex row of the label, first face row of the
+// (tile,label) block)
+__global__ void __launch_bounds__(256) k_tl_fixup(TLEntry* tl, const Control* ctl, u64 capL, const u64* offV,
+                                                  const u64* offT) {
+  u64 n = ctl->cur_tl;
+  if (n > capL) n = capL;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 a = tl[i].a;
+    const uint32_t gs = (uint32_t)a;
+    TLEntry e;
+    e.a = offV[gs];
+    e.b = offT[gs] + (a >> 32);
+    tl[i] = e;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// final gather: key -> float32 vertex (reference: unpack_* marching_cubes.hpp:114-135 with
-// offset 0, factor = captured resolution; then _normalize_mesh zmesh/_zmesh.pyx:423-433).
-// Three separately rounded float32 operations, no FMA contraction.
+// pass 2
 
-struct FinalizeArgs {
-  const unsigned long long* vkeys;
-  float* verts;
-  unsigned long long nV;
+struct Pass2Args {
+  const TileHdr* hdr;
+  const uint32_t* worklist;
+  const uint8_t* own6;
+  const uint32_t* rowbase;
+  const uint32_t* perm;
+  const uint16_t* vl;
+  const uint32_t* rec;
+  const TLEntry* tl;
+  uint32_t* faces;  // [T_total][3]
+  float* verts;     // [V_total][3]
+  float* normals;   // [V_total][3] or null
   float r0, r1, r2;  // captured resolution
   float c0, c1, c2;  // centering offset
-  int voxel_centered;
-  int transpose;
-};
-
-__device__ __forceinline__ void key_to_p(unsigned long long k, float r0, float r1, float r2, int transpose,
-                                         float& p0, float& p1, float& p2) {
-  float kx = __fadd_rn(0.0f, (float)(uint32_t)((k >> 42) & 0x1FFFFFull));
-  float ky = __fadd_rn(0.0f, (float)(uint32_t)((k >> 21) & 0x1FFFFFull));
-  float kz = __fadd_rn(0.0f, (float)(uint32_t)(k & 0x1FFFFFull));
-  if (transpose) {  // cMesher.hpp:128-138
-    p0 = __fmul_rn(r0, kz); p1 = __fmul_rn(r1, ky); p2 = __fmul_rn(r2, kx);
-  } else {          // cMesher.hpp:139-149
-    p0 = __fmul_rn(r0, kx); p1 = __fmul_rn(r1, ky); p2 = __fmul_rn(r2, kz);
-  }
-}
-
-__global__ void __launch_bounds__(256) k_finalize_vertices(const FinalizeArgs a) {
-  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (; i < a.nV; i += stride) {
-    float p0, p1, p2;
-    key_to_p(a.vkeys[i], a.r0, a.r1, a.r2, a.transpose, p0, p1, p2);
-    if (a.voxel_centered) { p0 = __fadd_rn(p0, a.c0); p1 = __fadd_rn(p1, a.c1); p2 = __fadd_rn(p2, a.c2); }
-    a.verts[3 * i + 0] = __fmul_rn(p0, 0.5f);  // == p / 2.0f exactly
-    a.verts[3 * i + 1] = __fmul_rn(p1, 0.5f);
-    a.verts[3 * i + 2] = __fmul_rn(p2, 0.5f);
-  }
-}
-
-// Normals (reference zmesh/chunk_mesh.hpp:345-384 on the pre-normalisation vertices res*k).
-struct NormalsArgs {
-  const unsigned long long* vkeys;
-  const uint32_t* faces;
-  float* normals;  // [nV][3], zeroed
-  const unsigned long long* voff;  // [nSlots] per label-table slot (non-decreasing)
-  const unsigned long long* foff;  // [nSlots]
-  unsigned long long nT, nV;
-  uint32_t nSlots;
-  float r0, r1, r2;
-  int transpose;
+  int voxel_centered, transpose;
+  int write_faces, write_verts, normalize;
 };
 
 __device__ __forceinline__ float len3(float x, float y, float z) {
@@ -789,34 +755,208 @@ __device__ __forceinline__ void face_normal_scatter(const float v0[3], const flo
   }
 }
 
-__global__ void __launch_bounds__(256) k_normals_accumulate(const NormalsArgs a) {
-  unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (; j < a.nT; j += stride) {
-    // table slot of face j: last i with foff[i] <= j (empty slots repeat the next live offset)
-    uint32_t lo = 0, hi = a.nSlots;
-    while (hi - lo > 1) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (a.foff[mid] <= j) lo = mid; else hi = mid;
+// p = res * k for the vertex on the edge of memory axis d owned by extended voxel (ef, em, es):
+// half-voxel key, memory axes -> logical axes, + shard origin (reference: unpack_*,
+// marching_cubes.hpp:114-135 with offset 0, factor = captured resolution; transpose = the legacy
+// get_mesh orientation, cMesher.hpp:128-149).
+template <bool CO>
+__device__ __forceinline__ void slot_position(const VolParams& vp, const Pass2Args& a, uint32_t ef, uint32_t em,
+                                              uint32_t es, uint32_t d, float& p0, float& p1, float& p2) {
+  const uint32_t hf = 2u * ef + (d == 0u), hm = 2u * em + (d == 1u), hs = 2u * es + (d == 2u);
+  const float kx = __fadd_rn(0.0f, (float)((CO ? hs : hf) + 2u * vp.ox));
+  const float ky = __fadd_rn(0.0f, (float)(hm + 2u * vp.oy));
+  const float kz = __fadd_rn(0.0f, (float)((CO ? hf : hs) + 2u * vp.oz));
+  if (a.transpose) { p0 = __fmul_rn(a.r0, kz); p1 = __fmul_rn(a.r1, ky); p2 = __fmul_rn(a.r2, kx); }
+  else             { p0 = __fmul_rn(a.r0, kx); p1 = __fmul_rn(a.r1, ky); p2 = __fmul_rn(a.r2, kz); }
+}
+
+// faces: one CTA per non-empty tile, one thread per (label, cube) record
+template <bool CO, bool NORMALS>
+__global__ void __launch_bounds__(NT) k_faces(const VolParams vp, const Pass2Args a) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  __shared__ uint32_t gb[RS * RM * RW];   // spatial id of the first slot of each region voxel
+  __shared__ uint8_t o6[RS * RM * RW];
+  __shared__ uint32_t cur[Caps<1>::LT];   // running face cursor per tile-local label
+  __shared__ u64 s_trinib[256];
+  __shared__ uint8_t s_tricount[256];
+  __shared__ uint32_t s_einfo[12];
+  __shared__ TileHdr s_hdr;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ltm = (1u << lane) - 1u;
+  const uint32_t tile = a.worklist[blockIdx.x];
+  if (tid == 0) s_hdr = a.hdr[tile];
+  __syncthreads();
+  const TileHdr h = s_hdr;
+  if (h.nrec == 0) return;
+
+  uint32_t b = tile;
+  const uint32_t tf = b % vp.ntf;
+  b /= vp.ntf;
+  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
+  const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
+
+  s_tricount[tid] = TRI_COUNT_D[tid];
+  s_trinib[tid] = TRI_NIBBLES_D[tid];
+  if (tid < 12) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) v = (tid == e) ? edge_info<CO>(e) : v;
+    s_einfo[tid] = v;
+  }
+  for (uint32_t i = tid; i < h.nlab; i += NT) cur[i] = 0u;
+
+  // own6 of the (TF+1)(TM+1)(TS+1) voxels whose slots the tile's cubes can reference, and the
+  // spatial id of each voxel's first slot
+  for (int r = warp; r < RM * RS; r += NW) {
+    const int lm = r % RM, ls = r / RM;
+    const uint32_t em = em0 + lm, es = es0 + ls;
+    const bool rowvalid = em < vp.Em && es < vp.Es;
+    const size_t row = (size_t)es * vp.Em + em;
+    uint32_t m = 0;
+    if (rowvalid) m = a.own6[row * vp.Efp + ef0 + lane];
+    uint32_t rowtotal = 0, pre = 0, rb = 0;
+    if (__ballot_sync(FULL, m != 0u)) {
+      pre = warp_prefix3(__popc(m), ltm, rowtotal);
+      if (lane == 0) rb = a.rowbase[row * vp.ntf + tf];
+      rb = __shfl_sync(FULL, rb, 0);
     }
-    const unsigned long long vb = a.voff[lo];
-    uint32_t f0 = a.faces[3 * j + 0], f1 = a.faces[3 * j + 1], f2 = a.faces[3 * j + 2];
-    if (a.transpose) { uint32_t t = f0; f0 = f2; f2 = t; }  // legacy faces (t0,t2,t1) = stored row reversed
-    float v0[3], v1[3], v2[3];
-    key_to_p(a.vkeys[vb + f0], a.r0, a.r1, a.r2, a.transpose, v0[0], v0[1], v0[2]);
-    key_to_p(a.vkeys[vb + f1], a.r0, a.r1, a.r2, a.transpose, v1[0], v1[1], v1[2]);
-    key_to_p(a.vkeys[vb + f2], a.r0, a.r1, a.r2, a.transpose, v2[0], v2[1], v2[2]);
-    face_normal_scatter(v0, v1, v2, a.normals + 3ull * (vb + f0), a.normals + 3ull * (vb + f1),
-                        a.normals + 3ull * (vb + f2));
+    o6[r * RW + lane] = (uint8_t)m;
+    gb[r * RW + lane] = rb + pre;
+    if (lane == 0) {  // halo column lf == TF: first voxel of the next tile's row
+      uint32_t m32 = 0, rb32 = 0;
+      if (rowvalid && tf + 1 < vp.ntf) {
+        m32 = a.own6[row * vp.Efp + ef0 + TF];
+        if (m32) rb32 = a.rowbase[row * vp.ntf + tf + 1];
+      }
+      o6[r * RW + TF] = (uint8_t)m32;
+      gb[r * RW + TF] = rb32;
+    }
+  }
+  __syncthreads();
+
+  const uint32_t nrec = h.nrec;
+  for (uint32_t base = warp * 32; base < nrec; base += NT) {
+    const uint32_t i = base + lane;
+    const bool valid = i < nrec;
+    const uint32_t w = valid ? a.rec[h.recbase + i] : 0u;
+    const uint32_t vidx = w & 0x7FFu, cs = (w >> 11) & 0xFFu, ci = w >> 19;
+    const uint32_t nt = valid ? s_tricount[cs] : 0u;
+    // warp-aggregated reservation of nt face rows in the (tile,label) block
+    const uint32_t grp = __match_any_sync(FULL, valid ? ci : 0xFFFFFFFFu);
+    uint32_t tot;
+    const uint32_t pre = group_prefix3(nt, grp, grp & ltm, tot);
+    const int leader = __ffs(grp) - 1;
+    uint32_t old = 0;
+    if (valid && lane == leader) old = atomicAdd(&cur[ci], tot);
+    old = __shfl_sync(FULL, old, leader);
+    if (!valid) continue;
+    const TLEntry e = a.tl[h.tlbase + ci];
+    const int lf = vidx & 31, lm = (vidx >> 5) & 7, ls = vidx >> 8;
+    const uint32_t u0 = (ls * RM + lm) * RW + lf;
+    const u64 nib = s_trinib[cs];
+    uint32_t* fout = a.faces + 3ull * (e.b + old + pre);
+    for (uint32_t t = 0; t < nt; ++t) {
+      uint32_t vi[3];
+      float p[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t ed = (uint32_t)(nib >> (12 * t + 4 * k)) & 0xFu;
+        const uint32_t info = s_einfo[ed];
+        const uint32_t u = u0 + (info & 0x3FFu);
+        const uint32_t d2 = (info >> 12) & 7u, oc = (info >> 16) & 7u;
+        // side 0: the owner (lower) voxel carries the label; side 1: the upper one does
+        const uint32_t slot = d2 + ((cs >> oc) & 1u);
+        const uint32_t g = gb[u] + __popc((uint32_t)o6[u] & ((1u << slot) - 1u));
+        vi[k] = __ldg(a.perm + g);
+        if (NORMALS)
+          slot_position<CO>(vp, a, ef0 + lf + ((info >> 20) & 1u), em0 + lm + ((info >> 21) & 1u),
+                            es0 + ls + ((info >> 22) & 1u), d2 >> 1, p[k][0], p[k][1], p[k][2]);
+      }
+      // reference winding of Mesher.get: (E[T[3n+1]], E[T[3n]], E[T[3n+2]])
+      // (marching_cubes.hpp:338-343 then cMesher.hpp:158-162)
+      if (a.write_faces) {
+        fout[3 * t + 0] = vi[1];
+        fout[3 * t + 1] = vi[0];
+        fout[3 * t + 2] = vi[2];
+      }
+      if (NORMALS) {
+        float* nb = a.normals + 3ull * e.a;
+        if (a.transpose)  // legacy faces (t0,t2,t1) = stored row reversed
+          face_normal_scatter(p[2], p[0], p[1], nb + 3ull * vi[2], nb + 3ull * vi[0], nb + 3ull * vi[1]);
+        else
+          face_normal_scatter(p[1], p[0], p[2], nb + 3ull * vi[1], nb + 3ull * vi[0], nb + 3ull * vi[2]);
+      }
+    }
   }
 }
 
+// vertices: one CTA per non-empty tile, one thread per owning voxel.  Final form (reference:
+// _normalize_mesh zmesh/_zmesh.pyx:423-433): three separately rounded float32 operations, no FMA.
+template <bool CO>
+__global__ void __launch_bounds__(NT) k_vertices(const VolParams vp, const Pass2Args a) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  __shared__ TileHdr s_hdr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ltm = (1u << lane) - 1u;
+  const uint32_t tile = a.worklist[blockIdx.x];
+  if (tid == 0) s_hdr = a.hdr[tile];
+  __syncthreads();
+  const TileHdr h = s_hdr;
+  if (h.nslots == 0) return;
+  uint32_t b = tile;
+  const uint32_t tf = b % vp.ntf;
+  b /= vp.ntf;
+  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
+  const uint32_t ef = tf * TF + lane, es = ts * TS + warp;
+  if (es >= vp.Es) return;
+  for (int j = 0; j < TM; ++j) {
+    const uint32_t em = tm * TM + j;
+    if (em >= vp.Em) break;
+    const size_t row = (size_t)es * vp.Em + em;
+    const uint32_t m = a.own6[row * vp.Efp + ef];
+    if (!__ballot_sync(FULL, m != 0u)) continue;
+    uint32_t rowtotal;
+    const uint32_t pre = warp_prefix3(__popc(m), ltm, rowtotal);
+    uint32_t rb = 0;
+    if (lane == 0) rb = a.rowbase[row * vp.ntf + tf];
+    rb = __shfl_sync(FULL, rb, 0);
+    uint32_t g = rb + pre;
+    uint32_t mm = m;
+    while (mm) {
+      const int s6 = __ffs(mm) - 1;
+      mm &= mm - 1u;
+      const uint32_t rank = __ldg(a.perm + g);
+      const uint32_t ci = __ldg(a.vl + g);
+      ++g;
+      const u64 dst = a.tl[h.tlbase + ci].a + rank;
+      if (a.write_verts) {
+        float p0, p1, p2;
+        slot_position<CO>(vp, a, ef, em, es, (uint32_t)s6 >> 1, p0, p1, p2);
+        if (a.voxel_centered) { p0 = __fadd_rn(p0, a.c0); p1 = __fadd_rn(p1, a.c1); p2 = __fadd_rn(p2, a.c2); }
+        float* v = a.verts + 3ull * dst;
+        v[0] = __fmul_rn(p0, 0.5f);  // == p / 2.0f exactly
+        v[1] = __fmul_rn(p1, 0.5f);
+        v[2] = __fmul_rn(p2, 0.5f);
+      }
+      if (a.normalize) {
+        float* nn = a.normals + 3ull * dst;
+        float x = nn[0], y = nn[1], z = nn[2];
+        const float l = len3(x, y, z);
+        if (l != 1.0f) { x = __fdiv_rn(x, l); y = __fdiv_rn(y, l); z = __fdiv_rn(z, l); }  // 0/0 -> NaN like hat()
+        nn[0] = x; nn[1] = y; nn[2] = z;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Mesher.compute_normals on an arbitrary float32 mesh (zmesh/_zmesh.pyx:138-152).
 __global__ void __launch_bounds__(256) k_normals_accumulate_f32(const float* __restrict__ verts,
                                                                const uint32_t* __restrict__ faces,
-                                                               unsigned long long nT, float* normals) {
-  unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+                                                               u64 nT, float* normals) {
+  u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
   for (; j < nT; j += stride) {
     const uint32_t f0 = faces[3 * j + 0], f1 = faces[3 * j + 1], f2 = faces[3 * j + 2];
     float v0[3], v1[3], v2[3];
@@ -830,9 +970,9 @@ __global__ void __launch_bounds__(256) k_normals_accumulate_f32(const float* __r
   }
 }
 
-__global__ void __launch_bounds__(256) k_normals_normalize(float* normals, unsigned long long nV) {
-  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+__global__ void __launch_bounds__(256) k_normals_normalize(float* normals, u64 nV) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
   for (; i < nV; i += stride) {
     float x = normals[3 * i], y = normals[3 * i + 1], z = normals[3 * i + 2];
     float l = len3(x, y, z);
@@ -844,9 +984,9 @@ __global__ void __launch_bounds__(256) k_normals_normalize(float* normals, unsig
 // ---------------------------------------------------------------------------------------------
 // synthetic jittered-grid Voronoi volume (benchmark/test input)
 
-__host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+__host__ __device__ __forceinline__ u64 splitmix64(u64 x) {
   x += 0x9E3779B97F4A7C15ull;
-  unsigned long long z = x;
+  u64 z = x;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
@@ -854,41 +994,41 @@ __host__ __device__ __forceinline__ unsigned long long splitmix64(unsigned long 
 
 struct SynthArgs {
   void* dst;
-  unsigned long long n;  // voxels of the block
-  uint32_t sx, sy, sz;   // block shape (logical)
-  uint32_t ox, oy, oz;   // block origin inside the full volume
-  uint32_t gx, gy, gz;   // cells per axis of the full volume
+  u64 n;                // voxels of the block
+  uint32_t sx, sy, sz;  // block shape (logical)
+  uint32_t ox, oy, oz;  // block origin inside the full volume
+  uint32_t gx, gy, gz;  // cells per axis of the full volume
   uint32_t pitch;
-  unsigned long long seed;
+  u64 seed;
   int c_order;
 };
 
 template <typename L>
 __global__ void __launch_bounds__(256) k_synth_voronoi(const SynthArgs a) {
-  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
   for (; i < a.n; i += stride) {
     uint32_t lx, ly, lz;
-    if (a.c_order) { lz = (uint32_t)(i % a.sz); unsigned long long t = i / a.sz; ly = (uint32_t)(t % a.sy); lx = (uint32_t)(t / a.sy); }
-    else           { lx = (uint32_t)(i % a.sx); unsigned long long t = i / a.sx; ly = (uint32_t)(t % a.sy); lz = (uint32_t)(t / a.sy); }
+    if (a.c_order) { lz = (uint32_t)(i % a.sz); u64 t = i / a.sz; ly = (uint32_t)(t % a.sy); lx = (uint32_t)(t / a.sy); }
+    else           { lx = (uint32_t)(i % a.sx); u64 t = i / a.sx; ly = (uint32_t)(t % a.sy); lz = (uint32_t)(t / a.sy); }
     const long long x = (long long)lx + a.ox, y = (long long)ly + a.oy, z = (long long)lz + a.oz;
     const int bi = (int)(x / a.pitch), bj = (int)(y / a.pitch), bk = (int)(z / a.pitch);
     long long best_d = 0x7FFFFFFFFFFFFFFFll;
-    unsigned long long best_c = 0;
+    u64 best_c = 0;
     for (int dk = -1; dk <= 1; ++dk)
       for (int dj = -1; dj <= 1; ++dj)
         for (int di = -1; di <= 1; ++di) {
           const int ni = bi + di, nj = bj + dj, nk = bk + dk;
           if (ni < 0 || nj < 0 || nk < 0 || ni >= (int)a.gx || nj >= (int)a.gy || nk >= (int)a.gz) continue;
-          const unsigned long long c = (unsigned long long)ni + (unsigned long long)a.gx * ((unsigned long long)nj + (unsigned long long)a.gy * nk);
-          const unsigned long long h = splitmix64(c ^ a.seed);
+          const u64 c = (u64)ni + (u64)a.gx * ((u64)nj + (u64)a.gy * nk);
+          const u64 h = splitmix64(c ^ a.seed);
           const long long sx = (long long)ni * a.pitch + (long long)(((h & 0xFFFFull) * a.pitch) >> 16);
           const long long sy = (long long)nj * a.pitch + (long long)((((h >> 16) & 0xFFFFull) * a.pitch) >> 16);
           const long long sz = (long long)nk * a.pitch + (long long)((((h >> 32) & 0xFFFFull) * a.pitch) >> 16);
           const long long d = (x - sx) * (x - sx) + (y - sy) * (y - sy) + (z - sz) * (z - sz);
           if (d < best_d || (d == best_d && c < best_c)) { best_d = d; best_c = c; }
         }
-    unsigned long long lab = sizeof(L) == 8 ? (splitmix64(best_c + 1ull) | 1ull) : (best_c + 1ull);
+    u64 lab = sizeof(L) == 8 ? (splitmix64(best_c + 1ull) | 1ull) : (best_c + 1ull);
     static_cast<L*>(a.dst)[i] = (L)lab;
   }
 }
