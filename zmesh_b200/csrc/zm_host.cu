@@ -67,7 +67,7 @@ struct zm_handle {
 
   // scratch + intermediates (device)
   DevBuf d_vol, d_keys, d_cnt, d_offV, d_offT, d_list, d_partial, d_ctl;
-  DevBuf d_own6, d_rowbase, d_perm, d_vl, d_rec, d_tl, d_hdr, d_worklist, d_dense;
+  DevBuf d_own6, d_rowbase, d_perm, d_vinfo, d_rec, d_tl, d_hdr, d_dense;
   // results (device)
   DevBuf d_faces, d_verts, d_normals;
   zm::Control* h_ctl = nullptr;  // pinned
@@ -192,6 +192,12 @@ int prepare_device(zm_handle* h) {
   ZM_CUDA(h, cudaMemcpyToSymbol(TRI_COUNT_D, TRI_COUNT, sizeof(TRI_COUNT)));
   static_assert(sizeof(TRI_NIBBLES) == 256 * sizeof(unsigned long long), "table size");
   ZM_CUDA(h, cudaMemcpyToSymbol(TRI_NIBBLES_D, TRI_NIBBLES, sizeof(TRI_NIBBLES)));
+  {
+    std::vector<uint16_t> tab(2 * 256 * 16);
+    build_case_table<false>(tab.data());
+    build_case_table<true>(tab.data() + 256 * 16);
+    ZM_CUDA(h, cudaMemcpyToSymbol(CASE_TAB_D, tab.data(), tab.size() * sizeof(uint16_t)));
+  }
   for (int lb : {1, 2, 4, 8})
     for (int co = 0; co < 2; ++co) {
       KernelSet ks = kernel_set(lb, co != 0);
@@ -276,7 +282,6 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   ZM_CUDA(h, h->d_own6.ensure((size_t)vp.Es * vp.Em * vp.Efp));
   ZM_CUDA(h, h->d_rowbase.ensure(nrows * sizeof(uint32_t)));
   ZM_CUDA(h, h->d_hdr.ensure((size_t)ntiles * sizeof(TileHdr)));
-  ZM_CUDA(h, h->d_worklist.ensure((size_t)ntiles * 4));
   ZM_CUDA(h, h->d_dense.ensure((size_t)ntiles * 4));
   ZM_CUDA(h, h->d_ctl.ensure(sizeof(Control)));
   ZM_CUDA(h, h->d_partial.ensure(3 * 1024 * 8));
@@ -298,7 +303,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
     ZM_CUDA(h, h->d_offT.ensure((size_t)cap * 8));
     ZM_CUDA(h, h->d_list.ensure((size_t)cap * 24));
     ZM_CUDA(h, h->d_perm.ensure((size_t)capV * 4));
-    ZM_CUDA(h, h->d_vl.ensure((size_t)capV * 2));
+    ZM_CUDA(h, h->d_vinfo.ensure((size_t)capV * 4));
     ZM_CUDA(h, h->d_rec.ensure((size_t)capR * 4));
     ZM_CUDA(h, h->d_tl.ensure((size_t)capL * sizeof(TLEntry)));
     ZM_CUDA(h, cudaMemsetAsync(h->d_keys.p, 0, (size_t)cap * 8, st));
@@ -307,8 +312,8 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
 
     LabelTable ht{h->d_keys.as<u64>(), h->d_cnt.as<u64>(), cap - 1};
     Pass1Args p1{ht, d_ctl, h->d_own6.as<uint8_t>(), h->d_rowbase.as<uint32_t>(), h->d_perm.as<uint32_t>(),
-                 h->d_vl.as<uint16_t>(), h->d_rec.as<uint32_t>(), h->d_tl.as<TLEntry>(), h->d_hdr.as<TileHdr>(),
-                 h->d_worklist.as<uint32_t>(), h->d_dense.as<uint32_t>(), capV, capR, capL};
+                 h->d_vinfo.as<uint32_t>(), h->d_rec.as<uint32_t>(), h->d_tl.as<TLEntry>(), h->d_hdr.as<TileHdr>(),
+                 h->d_dense.as<uint32_t>(), capV, capR, capL};
     ks.classify[0]<<<(uint32_t)ntiles, NT, ks.smem[0], st>>>(vp, tmap, p1);
     ZM_CUDA(h, cudaGetLastError());
     const uint32_t dense_grid = (uint32_t)std::min<unsigned long long>(ntiles, 148ull);
@@ -439,11 +444,10 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     }
     Pass2Args a{};
     a.hdr = h->d_hdr.as<TileHdr>();
-    a.worklist = h->d_worklist.as<uint32_t>();
     a.own6 = h->d_own6.as<uint8_t>();
     a.rowbase = h->d_rowbase.as<uint32_t>();
     a.perm = h->d_perm.as<uint32_t>();
-    a.vl = h->d_vl.as<uint16_t>();
+    a.vinfo = h->d_vinfo.as<uint32_t>();
     a.rec = h->d_rec.as<uint32_t>();
     a.tl = h->d_tl.as<TLEntry>();
     a.faces = h->d_faces.as<uint32_t>();
@@ -463,7 +467,7 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     }
     ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
     if (!same_verts || need_normals) {
-      vertices_kernel(h->c_order)<<<h->n_work, NT, 0, st>>>(h->vp, a);
+      vertices_kernel(h->c_order)<<<h->n_work, NT_V, 0, st>>>(h->vp, a);
       ZM_CUDA(h, cudaGetLastError());
       ++launches;
     }
@@ -536,7 +540,7 @@ void zm_destroy(zm_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_vol, &h->d_keys, &h->d_cnt, &h->d_offV, &h->d_offT, &h->d_list, &h->d_partial, &h->d_ctl,
-                    &h->d_own6, &h->d_rowbase, &h->d_perm, &h->d_vl, &h->d_rec, &h->d_tl, &h->d_hdr, &h->d_worklist,
+                    &h->d_own6, &h->d_rowbase, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_hdr,
                     &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals})
     b->release();
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -659,7 +663,7 @@ int zm_clear(zm_handle* h) {
   drop_results(h);
   h->has_result = had;  // a cleared mesher answers like an empty one (marching_cubes.hpp:184-189)
   cudaSetDevice(h->device);
-  for (DevBuf* b : {&h->d_faces, &h->d_verts, &h->d_normals, &h->d_perm, &h->d_vl, &h->d_rec, &h->d_tl, &h->d_own6,
+  for (DevBuf* b : {&h->d_faces, &h->d_verts, &h->d_normals, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_own6,
                     &h->d_rowbase, &h->d_vol})
     b->release();
   return ZM_OK;

@@ -19,7 +19,7 @@
 // warp-aggregated atomics, one global reservation per (tile,label).  Outputs, all label-free:
 //   own6[voxel] (1 B), rowbase[row], perm[g] (4 B/vertex), vl[g] (2 B/vertex: tile-local label
 //   index), rec[] (4 B per (label,cube) pair: cube-in-tile | case | tile-local label index),
-//   tl[] (per (tile,label): label slot + face base), hdr[tile], worklist of non-empty tiles.
+//   tl[] (per (tile,label): label slot + face base), hdr[] work list of the non-empty tiles.
 // Scan (k_scan_*) turns per-label counts into per-label output offsets; k_tl_fixup folds them into
 // tl[].  Pass 2 never touches labels again:
 //   k_faces    : one thread per record -> faces (uint32 triples) [+ face normals accumulation]
@@ -63,7 +63,7 @@ enum : uint32_t {
 // tiles that overflow it are queued and redone by the MODE 1 launch, whose capacities are the
 // hard maxima of a tile (so it cannot overflow).
 template <int MODE> struct Caps;
-template <> struct Caps<0> { static constexpr int LT = 512, VCAP = 4096, RCAP = 4096, PROBES = 32; };
+template <> struct Caps<0> { static constexpr int LT = 256, VCAP = 2048, RCAP = 2048, PROBES = 16; };
 template <> struct Caps<1> { static constexpr int LT = 4096, VCAP = 6 * TILE_VOX, RCAP = 8 * TILE_VOX, PROBES = 4096; };
 
 struct VolParams {
@@ -83,12 +83,14 @@ struct LabelTable {  // global open-addressing table, key 0 = empty (label 0 is 
   uint32_t mask;  // capacity - 1
 };
 
-struct __align__(8) TileHdr {
+struct __align__(16) TileHdr {  // one per non-empty tile, in work-list order
   u64 recbase;
   uint32_t gbase;
   uint32_t tlbase;
   uint16_t nslots, nrec, nlab, pad;
+  uint32_t tile, pad2;
 };
+static_assert(sizeof(TileHdr) == 32, "TileHdr is loaded as two 16-byte words");
 
 struct __align__(16) TLEntry {  // pass 1: a = label slot | face base in label << 32;  final: a = first
   u64 a, b;                     // vertex row of the label, b = first face row of this (tile,label)
@@ -107,11 +109,10 @@ struct Pass1Args {
   uint8_t* own6;      // [Es][Em][Efp]
   uint32_t* rowbase;  // [Es*Em*ntf]
   uint32_t* perm;     // [capV]
-  uint16_t* vl;       // [capV]
+  uint32_t* vinfo;    // [capV]: voxel-in-tile | slot << 11 | tile-local label index << 14
   uint32_t* rec;      // [capR]
   TLEntry* tl;        // [capL]
-  TileHdr* hdr;       // [ntiles]
-  uint32_t* worklist;    // [ntiles]
+  TileHdr* hdr;       // [ntiles] work list of non-empty tiles
   uint32_t* dense_list;  // [ntiles]
   u64 capV, capR, capL;
 };
@@ -135,8 +136,7 @@ template <bool CO> __host__ __device__ constexpr int corner_plus_f() { return CO
 template <bool CO> __host__ __device__ constexpr int corner_plus_m() { return 4; }
 template <bool CO> __host__ __device__ constexpr int corner_plus_s() { return CO ? 1 : 3; }
 
-// pass-2 staged own6 region: (TF+1) x (TM+1) x (TS+1) voxels, row pitch RW
-constexpr int RW = 36;
+// pass-2 staged own6 region: (TF+1) x (TM+1) x (TS+1) voxels, row pitch TF+1
 
 // per edge: bits 0-9 region index delta of the owner voxel, bits 12-14 2*axis, bits 16-18 owner
 // corner, bits 20-22 owner offset (f,m,s).  The midpoint M = corner_a + corner_b (half-voxel
@@ -152,7 +152,7 @@ __host__ __device__ constexpr uint32_t edge_info(int e) {
   int oc = 0;
   for (int n = 0; n < 8; ++n)
     if (corner_df<CO>(n) == of && corner_dm<CO>(n) == om && corner_ds<CO>(n) == os) oc = n;
-  int delta = (os * RM + om) * RW + of;
+  int delta = (os * RM + om) * (TF + 1) + of;
   return (uint32_t)(delta | ((2 * axis) << 12) | (oc << 16) | (of << 20) | (om << 21) | (os << 22));
 }
 
@@ -260,22 +260,97 @@ __device__ __forceinline__ uint32_t group_prefix3(uint32_t c, uint32_t grp, uint
 template <typename L, int MODE>
 struct __align__(128) P1Smem {
   static constexpr int RFP = RowPad<L>::value;
-  L lab[RS * RM * RFP];  // TMA destination: must stay first (128-byte aligned)
+  union {
+    struct {
+      L lab[RS * RM * RFP];       // TMA destination: must stay first (128-byte aligned)
+      uint32_t alist[TILE_VOX];   // active voxels: voxel-in-tile | own6 << 11 | in-row slot prefix << 17
+    };
+    struct {                      // live from S5 on, when lab/alist are dead
+      uint32_t lvb[Caps<MODE>::LT];   // first rank of the tile's vertices inside the label
+      uint16_t cidx[Caps<MODE>::LT];  // tile-local (compact) label index
+    };
+  };
   u64 lkeys[Caps<MODE>::LT];
   u64 mbar;
   u64 recbase;
   uint32_t lcnt[Caps<MODE>::LT];  // low 16: vertices of the label in this tile, high 16: triangles
-  uint32_t lvb[Caps<MODE>::LT];   // first rank of the tile's vertices inside the label
   uint32_t vstage[Caps<MODE>::VCAP];  // per tile-local slot: local rank << 12 | table slot
   uint32_t rstage[Caps<MODE>::RCAP];  // voxel-in-tile | case << 11 | table slot << 19
   uint32_t rowcnt[TM * TS], rowpre[TM * TS];
   uint32_t nact, nrec, nlab, nslots, overflow, ok, gbase, tlbase, ci, ttot;
-  uint16_t cidx[Caps<MODE>::LT];
-  uint16_t alist[TILE_VOX];
-  uint8_t o6s[TILE_VOX], pre8s[TILE_VOX], tricount[256];
+  uint16_t pstage[Caps<MODE>::VCAP];  // per tile-local slot: voxel-in-tile | slot << 11
+  uint8_t tricount[256];
 };
+static_assert(sizeof(P1Smem<u64, 1>) <= 227 * 1024 && sizeof(P1Smem<uint8_t, 1>) <= 227 * 1024, "dense mode must fit one SM");
 
 extern __shared__ __align__(128) unsigned char zm_dyn_smem[];
+
+// S1 of classify_tile.  Thread (lane = f, warp = s) marches over m keeping the four labels of the
+// previous row in registers: per step 4 shared loads and 4 label compares give the cube's
+// uniformity and the voxel's slot mask.  INTERIOR tiles (no volume boundary within reach) skip all
+// validity logic; a step whose 32 cubes are all uniform costs ~25 instructions.
+template <typename L, int MODE, bool INTERIOR>
+__device__ __forceinline__ void scan_tile(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const L* lab,
+                                          uint32_t ef0, uint32_t em0, uint32_t es0) {
+  constexpr int RFP = P1Smem<L, MODE>::RFP;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, ls = threadIdx.x >> 5;
+  const uint32_t ltm = (1u << lane) - 1u;
+  const uint32_t ef = ef0 + lane, es = es0 + ls;
+  const bool okf = INTERIOR || ef < vp.Ef, oks = INTERIOR || es < vp.Es;
+  const bool nf1 = INTERIOR || ef + 1 < vp.Ef, ns1 = INTERIOR || es + 1 < vp.Es;
+  const L* p = lab + (ls * RM) * RFP + lane;
+  L a = p[0], af = p[1], as_ = p[RM * RFP];
+  bool nef = a != af, nes = a != as_;
+  bool eq_row = !nef && !nes && a == p[RM * RFP + 1];  // the 4 corners of row j agree
+  bool za = a != 0, zf = af != 0, zs = as_ != 0;
+  uint8_t* orow = o.own6 + ((size_t)es * vp.Em + em0) * vp.Efp + ef;
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    p += RFP;
+    const L am = p[0], amf = p[1], ams = p[RM * RFP], amfs = p[RM * RFP + 1];
+    const bool nef2 = am != amf, nes2 = am != ams;
+    const bool eq_row2 = !nef2 && !nes2 && am == amfs;
+    const bool nem = a != am;
+    const bool zm = am != 0;
+    const bool okm = INTERIOR || em0 + j < vp.Em, nm1 = INTERIOR || em0 + j + 1 < vp.Em;
+    const bool uniform = eq_row && eq_row2 && !nem;
+    bool act;
+    uint32_t m = 0;
+    if (INTERIOR) {
+      act = !uniform;
+    } else {
+      const bool valid = okf && okm && oks;
+      if (valid) {
+        if (nf1 && nef) m |= (za ? 1u : 0u) | (zf ? 2u : 0u);
+        if (nm1 && nem) m |= (za ? 4u : 0u) | (zm ? 8u : 0u);
+        if (ns1 && nes) m |= (za ? 16u : 0u) | (zs ? 32u : 0u);
+      }
+      act = (m != 0u) || (valid && nf1 && nm1 && ns1 && !uniform);
+    }
+    const uint32_t ab = __ballot_sync(FULL, act);
+    uint32_t rowtotal = 0;
+    if (ab) {
+      if (INTERIOR) {
+        if (nef) m |= (za ? 1u : 0u) | (zf ? 2u : 0u);
+        if (nem) m |= (za ? 4u : 0u) | (zm ? 8u : 0u);
+        if (nes) m |= (za ? 16u : 0u) | (zs ? 32u : 0u);
+      }
+      uint32_t pre = 0;
+      if (__ballot_sync(FULL, m != 0u)) pre = warp_prefix3(__popc(m), ltm, rowtotal);
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&S.nact, (uint32_t)__popc(ab));
+      base = __shfl_sync(FULL, base, 0);
+      if (act) S.alist[base + __popc(ab & ltm)] = (uint32_t)((ls * TM + j) * TF + lane) | (m << 11) | (pre << 17);
+    }
+    if (okm && oks) *orow = (uint8_t)m;
+    orow += vp.Efp;
+    if (lane == 0) S.rowcnt[ls * TM + j] = rowtotal;
+    a = am; af = amf; as_ = ams;
+    nef = nef2; nes = nes2; eq_row = eq_row2;
+    za = zm; zf = amf != 0; zs = ams != 0;
+  }
+}
 
 template <typename L, bool CO, int MODE>
 __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtensorMap* tmap, const Pass1Args& o,
@@ -325,49 +400,10 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
   __syncthreads();
 
   // ---- S1: slot masks, in-row prefixes, compaction of active voxels ----
-  {
-    const int ls = warp;
-    const uint32_t ef = ef0 + lane, es = es0 + ls;
-    const bool okf = ef < vp.Ef, oks = es < vp.Es, nf1 = ef + 1 < vp.Ef, ns1 = es + 1 < vp.Es;
-    const int i0 = (ls * RM) * RFP + lane;
-    L a = lab[i0], af = lab[i0 + 1], as_ = lab[i0 + RM * RFP], afs = lab[i0 + RM * RFP + 1];
-#pragma unroll
-    for (int j = 0; j < TM; ++j) {
-      const int in = (ls * RM + j + 1) * RFP + lane;
-      const L am = lab[in], afm = lab[in + 1], ams = lab[in + RM * RFP], afms = lab[in + RM * RFP + 1];
-      const uint32_t em = em0 + j;
-      const bool okm = em < vp.Em, nm1 = em + 1 < vp.Em;
-      const bool valid = okf && okm && oks;
-      uint32_t m = 0;
-      if (valid) {
-        if (nf1 && a != af) m |= (a != 0 ? 1u : 0u) | (af != 0 ? 2u : 0u);
-        if (nm1 && a != am) m |= (a != 0 ? 4u : 0u) | (am != 0 ? 8u : 0u);
-        if (ns1 && a != as_) m |= (a != 0 ? 16u : 0u) | (as_ != 0 ? 32u : 0u);
-      }
-      const bool cube = valid && nf1 && nm1 && ns1;
-      const bool uniform = a == af && a == am && a == as_ && a == afm && a == afs && a == ams && a == afms;
-      const bool act = (m != 0u) || (cube && !uniform);
-      if (okm && oks) o.own6[((size_t)es * vp.Em + em) * vp.Efp + ef] = (uint8_t)m;
-      const int vidx = (ls * TM + j) * TF + lane;
-      uint32_t rowtotal = 0;
-      if (__ballot_sync(FULL, m != 0u)) {
-        const uint32_t pre = warp_prefix3(__popc(m), ltm, rowtotal);
-        S.o6s[vidx] = (uint8_t)m;
-        S.pre8s[vidx] = (uint8_t)pre;
-      } else if (act) {
-        S.o6s[vidx] = 0;
-      }
-      if (lane == 0) S.rowcnt[ls * TM + j] = rowtotal;
-      const uint32_t ab = __ballot_sync(FULL, act);
-      if (ab) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&S.nact, (uint32_t)__popc(ab));
-        base = __shfl_sync(FULL, base, 0);
-        if (act) S.alist[base + __popc(ab & ltm)] = (uint16_t)vidx;
-      }
-      a = am; af = afm; as_ = ams; afs = afms;
-    }
-  }
+  if (ef0 + TF + 1 <= vp.Ef && em0 + TM + 1 <= vp.Em && es0 + TS + 1 <= vp.Es)
+    scan_tile<L, MODE, true>(vp, o, S, lab, ef0, em0, es0);
+  else
+    scan_tile<L, MODE, false>(vp, o, S, lab, ef0, em0, es0);
   __syncthreads();
 
   // ---- S2: row bases inside the tile ----
@@ -396,15 +432,16 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
   for (uint32_t base = warp * 32; base < nact; base += NT) {
     const uint32_t i = base + lane;
     const bool valid = i < nact;
-    const uint32_t vidx = valid ? S.alist[i] : 0u;
+    const uint32_t aw = valid ? S.alist[i] : 0u;
+    const uint32_t vidx = aw & 0x7FFu;
     const int lf = vidx & 31, lm = (vidx >> 5) & 7, ls = vidx >> 8;
     L c[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
       c[n] = lab[((ls + corner_ds<CO>(n)) * RM + (lm + corner_dm<CO>(n))) * RFP + (lf + corner_df<CO>(n))];
-    const uint32_t m = valid ? S.o6s[vidx] : 0u;
+    const uint32_t m = (aw >> 11) & 63u;
     const bool cube = (ef0 + lf + 1 < vp.Ef) && (em0 + lm + 1 < vp.Em) && (es0 + ls + 1 < vp.Es);
-    const uint32_t gl0 = m ? S.rowpre[ls * TM + lm] + S.pre8s[vidx] : 0u;
+    const uint32_t gl0 = S.rowpre[vidx >> 5] + (aw >> 17);
     uint32_t acc = valid ? 0u : 0xFFu;
     while (__any_sync(FULL, acc != 0xFFu)) {
       const bool have = acc != 0xFFu;
@@ -449,6 +486,7 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
           mm &= mm - 1u;
           const uint32_t lg = gl0 + __popc(m & ((1u << s6) - 1u));
           S.vstage[lg] = (r << 12) | (uint32_t)hs;
+          S.pstage[lg] = (uint16_t)(vidx | ((uint32_t)s6 << 11));
           ++r;
         }
       }
@@ -493,7 +531,6 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
     const bool ok = gbase + nslots <= o.capV && recbase + nrec <= o.capR && tlbase + nlab <= o.capL;
     if (!ok) atomicOr(&o.ctl->flags, FLAG_CAP);
     else {
-      o.worklist[atomicAdd(&o.ctl->work_count, 1u)] = tile;
       TileHdr h;
       h.recbase = recbase;
       h.gbase = (uint32_t)gbase;
@@ -502,7 +539,9 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
       h.nrec = (uint16_t)nrec;
       h.nlab = (uint16_t)nlab;
       h.pad = 0;
-      o.hdr[tile] = h;
+      h.tile = tile;
+      h.pad2 = 0;
+      o.hdr[atomicAdd(&o.ctl->work_count, 1u)] = h;
     }
     S.gbase = (uint32_t)gbase;
     S.recbase = recbase;
@@ -543,7 +582,7 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
     const uint32_t w = S.vstage[i];
     const uint32_t hs = w & 0xFFFu;
     o.perm[(size_t)gbase + i] = S.lvb[hs] + (w >> 12);
-    o.vl[(size_t)gbase + i] = S.cidx[hs];
+    o.vinfo[(size_t)gbase + i] = (uint32_t)S.pstage[i] | ((uint32_t)S.cidx[hs] << 14);
   }
   const uint32_t nrec = S.nrec;
   for (uint32_t i = tid; i < nrec; i += NT) {
@@ -708,11 +747,10 @@ __global__ void __launch_bounds__(256) k_tl_fixup(TLEntry* tl, const Control* ct
 
 struct Pass2Args {
   const TileHdr* hdr;
-  const uint32_t* worklist;
   const uint8_t* own6;
   const uint32_t* rowbase;
   const uint32_t* perm;
-  const uint16_t* vl;
+  const uint32_t* vinfo;
   const uint32_t* rec;
   const TLEntry* tl;
   uint32_t* faces;  // [T_total][3]
@@ -755,6 +793,28 @@ __device__ __forceinline__ void face_normal_scatter(const float v0[3], const flo
   }
 }
 
+// The contribution of one face to ONE of its corners (same arithmetic as face_normal_scatter).
+__device__ __forceinline__ void face_normal_corner(const float v0[3], const float v1[3], const float v2[3], int k,
+                                                   float* dst) {
+  float c[3], e1[3], e2[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    c[d] = __fdiv_rn(__fadd_rn(__fadd_rn(v0[d], v1[d]), v2[d]), 3.0f);
+    e1[d] = __fsub_rn(v1[d], v0[d]);
+    e2[d] = __fsub_rn(v2[d], v0[d]);
+  }
+  float n0 = __fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1]));
+  float n1 = __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2]));
+  float n2 = __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0]));
+  const float l = len3(n0, n1, n2);
+  if (l != 1.0f) { n0 = __fdiv_rn(n0, l); n1 = __fdiv_rn(n1, l); n2 = __fdiv_rn(n2, l); }
+  const float* vk = k == 0 ? v0 : (k == 1 ? v1 : v2);
+  const float w = len3(__fsub_rn(vk[0], c[0]), __fsub_rn(vk[1], c[1]), __fsub_rn(vk[2], c[2]));
+  atomicAdd(dst + 0, __fmul_rn(n0, w));
+  atomicAdd(dst + 1, __fmul_rn(n1, w));
+  atomicAdd(dst + 2, __fmul_rn(n2, w));
+}
+
 // p = res * k for the vertex on the edge of memory axis d owned by extended voxel (ef, em, es):
 // half-voxel key, memory axes -> logical axes, + shard origin (reference: unpack_*,
 // marching_cubes.hpp:114-135 with offset 0, factor = captured resolution; transpose = the legacy
@@ -770,67 +830,108 @@ __device__ __forceinline__ void slot_position(const VolParams& vp, const Pass2Ar
   else             { p0 = __fmul_rn(a.r0, kx); p1 = __fmul_rn(a.r1, ky); p2 = __fmul_rn(a.r2, kz); }
 }
 
-// faces: one CTA per non-empty tile, one thread per (label, cube) record
+// per (case, output corner) of the triangle table: region index delta of the owner voxel (9 bits) |
+// slot << 9 | owner offset (f,m,s) << 12; rows of 16 entries, triangle t at [3t, 3t+3) in the
+// reference winding of Mesher.get: (E[T[3n+1]], E[T[3n]], E[T[3n+2]])
+// (marching_cubes.hpp:338-343 then cMesher.hpp:158-162).  Filled by prepare_device.
+__device__ __align__(16) uint16_t CASE_TAB_D[2][256 * 16];
+
+template <bool CO>
+inline void build_case_table(uint16_t* tab) {
+  uint32_t info[12];
+  for (int e = 0; e < 12; ++e) info[e] = edge_info<CO>(e);
+  static const int order[3] = {1, 0, 2};
+  for (int cs = 0; cs < 256; ++cs)
+    for (int t = 0; t < 5; ++t)
+      for (int k = 0; k < 3; ++k) {
+        const int ed = (int)((TRI_NIBBLES[cs] >> (12 * t + 4 * order[k])) & 0xFull);
+        uint16_t v = 0;
+        if (t < TRI_COUNT[cs] && ed < 12) {
+          const uint32_t i = info[ed];
+          const uint32_t slot = ((i >> 12) & 7u) + (((uint32_t)cs >> ((i >> 16) & 7u)) & 1u);
+          v = (uint16_t)((i & 0x1FFu) | (slot << 9) | (((i >> 20) & 7u) << 12));
+        }
+        tab[cs * 16 + 3 * t + k] = v;
+      }
+}
+
+__device__ __forceinline__ TileHdr load_hdr(const TileHdr* p) {
+  union { uint4 q[2]; TileHdr h; } u;
+  u.q[0] = __ldg(reinterpret_cast<const uint4*>(p));
+  u.q[1] = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  return u.h;
+}
+
+// faces: one CTA per non-empty tile.  Records are read 32 per warp; their triangles are expanded
+// into (triangle, corner) items so that every lane does exactly one vertex lookup and one 4-byte
+// store, consecutive lanes writing consecutive words of the face array.
+constexpr int FW = TF + 1;  // row pitch of the staged own6 region
 template <bool CO, bool NORMALS>
-__global__ void __launch_bounds__(NT) k_faces(const VolParams vp, const Pass2Args a) {
+__global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams vp, const Pass2Args a) {
   constexpr uint32_t FULL = 0xffffffffu;
-  __shared__ uint32_t gb[RS * RM * RW];   // spatial id of the first slot of each region voxel
-  __shared__ uint8_t o6[RS * RM * RW];
-  __shared__ uint32_t cur[Caps<1>::LT];   // running face cursor per tile-local label
-  __shared__ u64 s_trinib[256];
+  constexpr int NROW = RM * RS;                   // 81 rows of TF+1 voxels
+  constexpr int RPW = (NROW + NW - 1) / NW;       // rows per warp
+  __shared__ uint32_t gb[NROW * FW];      // spatial id of the first slot of each region voxel
+  __shared__ uint8_t o6[NROW * FW];
+  __shared__ uint32_t cur[Caps<1>::LT / 2];  // running face cursors per tile-local label, two 16-bit halves per word
+  __shared__ __align__(16) uint16_t s_tab[256 * 16];
   __shared__ uint8_t s_tricount[256];
-  __shared__ uint32_t s_einfo[12];
-  __shared__ TileHdr s_hdr;
+  __shared__ u64 rf[NW][32];              // per record of the warp's batch: first face row
+  __shared__ u64 rv[NW][32];              //                                  first vertex row of the label
+  __shared__ uint32_t ru[NW][32];         //                                  region index | case << 16
+  __shared__ uint8_t tlist[NW][160];      // triangles of the batch: record lane << 3 | t
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ltm = (1u << lane) - 1u;
-  const uint32_t tile = a.worklist[blockIdx.x];
-  if (tid == 0) s_hdr = a.hdr[tile];
-  __syncthreads();
-  const TileHdr h = s_hdr;
+  const TileHdr h = load_hdr(a.hdr + blockIdx.x);
   if (h.nrec == 0) return;
-
-  uint32_t b = tile;
+  uint32_t b = h.tile;
   const uint32_t tf = b % vp.ntf;
   b /= vp.ntf;
   const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
   const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
 
+  // own6 of the (TF+1)(TM+1)(TS+1) voxels whose slots the tile's cubes can reference and the
+  // spatial id of each voxel's first slot; all loads of a warp are issued before any is used
   s_tricount[tid] = TRI_COUNT_D[tid];
-  s_trinib[tid] = TRI_NIBBLES_D[tid];
-  if (tid < 12) {
-    uint32_t v = 0;
-#pragma unroll
-    for (int e = 0; e < 12; ++e) v = (tid == e) ? edge_info<CO>(e) : v;
-    s_einfo[tid] = v;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(CASE_TAB_D[CO ? 1 : 0]);
+    uint4* dst = reinterpret_cast<uint4*>(s_tab);
+    dst[tid] = src[tid];
+    dst[tid + NT] = src[tid + NT];
   }
-  for (uint32_t i = tid; i < h.nlab; i += NT) cur[i] = 0u;
-
-  // own6 of the (TF+1)(TM+1)(TS+1) voxels whose slots the tile's cubes can reference, and the
-  // spatial id of each voxel's first slot
-  for (int r = warp; r < RM * RS; r += NW) {
-    const int lm = r % RM, ls = r / RM;
-    const uint32_t em = em0 + lm, es = es0 + ls;
-    const bool rowvalid = em < vp.Em && es < vp.Es;
-    const size_t row = (size_t)es * vp.Em + em;
-    uint32_t m = 0;
-    if (rowvalid) m = a.own6[row * vp.Efp + ef0 + lane];
-    uint32_t rowtotal = 0, pre = 0, rb = 0;
-    if (__ballot_sync(FULL, m != 0u)) {
-      pre = warp_prefix3(__popc(m), ltm, rowtotal);
-      if (lane == 0) rb = a.rowbase[row * vp.ntf + tf];
-      rb = __shfl_sync(FULL, rb, 0);
+  for (uint32_t i = tid; i < (h.nlab + 1u) / 2u; i += NT) cur[i] = 0u;
+  const bool more = tf + 1 < vp.ntf;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    constexpr int HB = (RPW + 1) / 2;
+    uint32_t mrow[HB], rbrow[HB], mh[HB], rbh[HB];
+#pragma unroll
+    for (int i = 0; i < HB; ++i) {
+      const int r = warp + NW * (half * HB + i);
+      const int ls = r / RM, lm = r - ls * RM;
+      const uint32_t em = em0 + lm, es = es0 + ls;
+      const bool rowvalid = r < NROW && em < vp.Em && es < vp.Es;
+      const size_t row = (size_t)es * vp.Em + em;
+      mrow[i] = rowvalid ? a.own6[row * vp.Efp + ef0 + lane] : 0u;
+      rbrow[i] = rowvalid ? __ldg(a.rowbase + row * vp.ntf + tf) : 0u;
+      mh[i] = (rowvalid && more) ? a.own6[row * vp.Efp + ef0 + TF] : 0u;  // halo column: next tile's first voxel
+      rbh[i] = (rowvalid && more) ? __ldg(a.rowbase + row * vp.ntf + tf + 1) : 0u;
     }
-    o6[r * RW + lane] = (uint8_t)m;
-    gb[r * RW + lane] = rb + pre;
-    if (lane == 0) {  // halo column lf == TF: first voxel of the next tile's row
-      uint32_t m32 = 0, rb32 = 0;
-      if (rowvalid && tf + 1 < vp.ntf) {
-        m32 = a.own6[row * vp.Efp + ef0 + TF];
-        if (m32) rb32 = a.rowbase[row * vp.ntf + tf + 1];
+#pragma unroll
+    for (int i = 0; i < HB; ++i) {
+      const int r = warp + NW * (half * HB + i);
+      if (r < NROW) {
+        const uint32_t m = mrow[i];
+        uint32_t pre = 0, rowtotal;
+        if (__ballot_sync(FULL, m != 0u)) pre = warp_prefix3(__popc(m), ltm, rowtotal);
+        o6[r * FW + lane] = (uint8_t)m;
+        gb[r * FW + lane] = rbrow[i] + pre;
+        if (lane == 0) {
+          o6[r * FW + TF] = (uint8_t)mh[i];
+          gb[r * FW + TF] = rbh[i];
+        }
       }
-      o6[r * RW + TF] = (uint8_t)m32;
-      gb[r * RW + TF] = rb32;
     }
   }
   __syncthreads();
@@ -839,7 +940,7 @@ __global__ void __launch_bounds__(NT) k_faces(const VolParams vp, const Pass2Arg
   for (uint32_t base = warp * 32; base < nrec; base += NT) {
     const uint32_t i = base + lane;
     const bool valid = i < nrec;
-    const uint32_t w = valid ? a.rec[h.recbase + i] : 0u;
+    const uint32_t w = valid ? __ldg(a.rec + h.recbase + i) : 0u;
     const uint32_t vidx = w & 0x7FFu, cs = (w >> 11) & 0xFFu, ci = w >> 19;
     const uint32_t nt = valid ? s_tricount[cs] : 0u;
     // warp-aggregated reservation of nt face rows in the (tile,label) block
@@ -847,105 +948,90 @@ __global__ void __launch_bounds__(NT) k_faces(const VolParams vp, const Pass2Arg
     uint32_t tot;
     const uint32_t pre = group_prefix3(nt, grp, grp & ltm, tot);
     const int leader = __ffs(grp) - 1;
+    const uint32_t sh = (ci & 1u) * 16u;
     uint32_t old = 0;
-    if (valid && lane == leader) old = atomicAdd(&cur[ci], tot);
-    old = __shfl_sync(FULL, old, leader);
-    if (!valid) continue;
-    const TLEntry e = a.tl[h.tlbase + ci];
-    const int lf = vidx & 31, lm = (vidx >> 5) & 7, ls = vidx >> 8;
-    const uint32_t u0 = (ls * RM + lm) * RW + lf;
-    const u64 nib = s_trinib[cs];
-    uint32_t* fout = a.faces + 3ull * (e.b + old + pre);
-    for (uint32_t t = 0; t < nt; ++t) {
-      uint32_t vi[3];
-      float p[3][3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const uint32_t ed = (uint32_t)(nib >> (12 * t + 4 * k)) & 0xFu;
-        const uint32_t info = s_einfo[ed];
-        const uint32_t u = u0 + (info & 0x3FFu);
-        const uint32_t d2 = (info >> 12) & 7u, oc = (info >> 16) & 7u;
-        // side 0: the owner (lower) voxel carries the label; side 1: the upper one does
-        const uint32_t slot = d2 + ((cs >> oc) & 1u);
-        const uint32_t g = gb[u] + __popc((uint32_t)o6[u] & ((1u << slot) - 1u));
-        vi[k] = __ldg(a.perm + g);
-        if (NORMALS)
-          slot_position<CO>(vp, a, ef0 + lf + ((info >> 20) & 1u), em0 + lm + ((info >> 21) & 1u),
-                            es0 + ls + ((info >> 22) & 1u), d2 >> 1, p[k][0], p[k][1], p[k][2]);
-      }
-      // reference winding of Mesher.get: (E[T[3n+1]], E[T[3n]], E[T[3n+2]])
-      // (marching_cubes.hpp:338-343 then cMesher.hpp:158-162)
-      if (a.write_faces) {
-        fout[3 * t + 0] = vi[1];
-        fout[3 * t + 1] = vi[0];
-        fout[3 * t + 2] = vi[2];
-      }
+    if (valid && lane == leader) old = atomicAdd(&cur[ci >> 1], tot << sh);
+    old = (__shfl_sync(FULL, old, leader) >> sh) & 0xFFFFu;
+    uint32_t ntot;
+    const uint32_t tpre = warp_prefix3(nt, ltm, ntot);
+    if (valid) {
+      const TLEntry e = a.tl[h.tlbase + ci];
+      const uint32_t lf = vidx & 31u, lm = (vidx >> 5) & 7u, ls = vidx >> 8;
+      ru[warp][lane] = ((ls * RM + lm) * FW + lf) | (cs << 16);
+      rf[warp][lane] = e.b + old + pre;
+      if (NORMALS) rv[warp][lane] = e.a;
+      for (uint32_t t = 0; t < nt; ++t) tlist[warp][tpre + t] = (uint8_t)((lane << 3) | t);
+    }
+    __syncwarp();
+    for (uint32_t j = lane; j < 3u * ntot; j += 32) {
+      const uint32_t q = (j * 171u) >> 9;  // j / 3 for j < 512
+      const uint32_t k = j - 3u * q;
+      const uint32_t tr = tlist[warp][q];
+      const uint32_t src = tr >> 3, t = tr & 7u;
+      const uint32_t uc = ru[warp][src];
+      const uint32_t u0 = uc & 0xFFFFu, rcs = uc >> 16;
+      const uint16_t* tab = s_tab + rcs * 16 + 3u * t;
+      const uint32_t en = tab[k];
+      const uint32_t u = u0 + (en & 0x1FFu);
+      // slot = 2*axis + side; side 0: the owner (lower) voxel carries the label, 1: the upper one
+      const uint32_t slot = (en >> 9) & 7u;
+      const uint32_t g = gb[u] + __popc((uint32_t)o6[u] & ((1u << slot) - 1u));
+      const uint32_t vi = __ldg(a.perm + g);
+      if (a.write_faces) a.faces[3ull * (rf[warp][src] + t) + k] = vi;
       if (NORMALS) {
-        float* nb = a.normals + 3ull * e.a;
-        if (a.transpose)  // legacy faces (t0,t2,t1) = stored row reversed
-          face_normal_scatter(p[2], p[0], p[1], nb + 3ull * vi[2], nb + 3ull * vi[0], nb + 3ull * vi[1]);
-        else
-          face_normal_scatter(p[1], p[0], p[2], nb + 3ull * vi[1], nb + 3ull * vi[0], nb + 3ull * vi[2]);
+        // the lane owning corner k recomputes the face normal from the cube geometry (no loads)
+        const uint32_t ls = u0 / (RM * FW), rem = u0 - ls * (RM * FW), lm = rem / FW, lf = rem - lm * FW;
+        float p[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint32_t ec = tab[c];
+          slot_position<CO>(vp, a, ef0 + lf + ((ec >> 12) & 1u), em0 + lm + ((ec >> 13) & 1u),
+                            es0 + ls + ((ec >> 14) & 1u), ((ec >> 9) & 7u) >> 1, p[c][0], p[c][1], p[c][2]);
+        }
+        float* dst = a.normals + 3ull * (rv[warp][src] + vi);
+        // legacy faces (t0,t2,t1) = the stored row reversed: corner k becomes corner 2-k
+        if (a.transpose) face_normal_corner(p[2], p[1], p[0], 2 - (int)k, dst);
+        else face_normal_corner(p[0], p[1], p[2], (int)k, dst);
       }
     }
+    __syncwarp();
   }
 }
 
-// vertices: one CTA per non-empty tile, one thread per owning voxel.  Final form (reference:
-// _normalize_mesh zmesh/_zmesh.pyx:423-433): three separately rounded float32 operations, no FMA.
+// vertices: one CTA per non-empty tile, one thread per vertex slot of the tile (perm/vinfo are
+// read coalesced).  Final form (reference: _normalize_mesh zmesh/_zmesh.pyx:423-433): three
+// separately rounded float32 operations, no FMA.
+constexpr int NT_V = 128;
 template <bool CO>
-__global__ void __launch_bounds__(NT) k_vertices(const VolParams vp, const Pass2Args a) {
-  constexpr uint32_t FULL = 0xffffffffu;
-  __shared__ TileHdr s_hdr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t ltm = (1u << lane) - 1u;
-  const uint32_t tile = a.worklist[blockIdx.x];
-  if (tid == 0) s_hdr = a.hdr[tile];
-  __syncthreads();
-  const TileHdr h = s_hdr;
+__global__ void __launch_bounds__(NT_V) k_vertices(const VolParams vp, const Pass2Args a) {
+  const TileHdr h = load_hdr(a.hdr + blockIdx.x);
   if (h.nslots == 0) return;
-  uint32_t b = tile;
+  uint32_t b = h.tile;
   const uint32_t tf = b % vp.ntf;
   b /= vp.ntf;
   const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
-  const uint32_t ef = tf * TF + lane, es = ts * TS + warp;
-  if (es >= vp.Es) return;
-  for (int j = 0; j < TM; ++j) {
-    const uint32_t em = tm * TM + j;
-    if (em >= vp.Em) break;
-    const size_t row = (size_t)es * vp.Em + em;
-    const uint32_t m = a.own6[row * vp.Efp + ef];
-    if (!__ballot_sync(FULL, m != 0u)) continue;
-    uint32_t rowtotal;
-    const uint32_t pre = warp_prefix3(__popc(m), ltm, rowtotal);
-    uint32_t rb = 0;
-    if (lane == 0) rb = a.rowbase[row * vp.ntf + tf];
-    rb = __shfl_sync(FULL, rb, 0);
-    uint32_t g = rb + pre;
-    uint32_t mm = m;
-    while (mm) {
-      const int s6 = __ffs(mm) - 1;
-      mm &= mm - 1u;
-      const uint32_t rank = __ldg(a.perm + g);
-      const uint32_t ci = __ldg(a.vl + g);
-      ++g;
-      const u64 dst = a.tl[h.tlbase + ci].a + rank;
-      if (a.write_verts) {
-        float p0, p1, p2;
-        slot_position<CO>(vp, a, ef, em, es, (uint32_t)s6 >> 1, p0, p1, p2);
-        if (a.voxel_centered) { p0 = __fadd_rn(p0, a.c0); p1 = __fadd_rn(p1, a.c1); p2 = __fadd_rn(p2, a.c2); }
-        float* v = a.verts + 3ull * dst;
-        v[0] = __fmul_rn(p0, 0.5f);  // == p / 2.0f exactly
-        v[1] = __fmul_rn(p1, 0.5f);
-        v[2] = __fmul_rn(p2, 0.5f);
-      }
-      if (a.normalize) {
-        float* nn = a.normals + 3ull * dst;
-        float x = nn[0], y = nn[1], z = nn[2];
-        const float l = len3(x, y, z);
-        if (l != 1.0f) { x = __fdiv_rn(x, l); y = __fdiv_rn(y, l); z = __fdiv_rn(z, l); }  // 0/0 -> NaN like hat()
-        nn[0] = x; nn[1] = y; nn[2] = z;
-      }
+  const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
+  const TLEntry* tl = a.tl + h.tlbase;
+  for (uint32_t i = threadIdx.x; i < h.nslots; i += NT_V) {
+    const uint32_t rank = __ldg(a.perm + h.gbase + i);
+    const uint32_t w = __ldg(a.vinfo + h.gbase + i);
+    const uint32_t vidx = w & 0x7FFu, s6 = (w >> 11) & 7u, ci = w >> 14;
+    const u64 dst = tl[ci].a + rank;
+    if (a.write_verts) {
+      float p0, p1, p2;
+      slot_position<CO>(vp, a, ef0 + (vidx & 31u), em0 + ((vidx >> 5) & 7u), es0 + (vidx >> 8), s6 >> 1, p0, p1, p2);
+      if (a.voxel_centered) { p0 = __fadd_rn(p0, a.c0); p1 = __fadd_rn(p1, a.c1); p2 = __fadd_rn(p2, a.c2); }
+      float* v = a.verts + 3ull * dst;
+      v[0] = __fmul_rn(p0, 0.5f);  // == p / 2.0f exactly
+      v[1] = __fmul_rn(p1, 0.5f);
+      v[2] = __fmul_rn(p2, 0.5f);
+    }
+    if (a.normalize) {
+      float* nn = a.normals + 3ull * dst;
+      float x = nn[0], y = nn[1], z = nn[2];
+      const float l = len3(x, y, z);
+      if (l != 1.0f) { x = __fdiv_rn(x, l); y = __fdiv_rn(y, l); z = __fdiv_rn(z, l); }  // 0/0 -> NaN like hat()
+      nn[0] = x; nn[1] = y; nn[2] = z;
     }
   }
 }
