@@ -63,11 +63,40 @@ int zm_set_resolution(zm_handle* h, const float resolution[3]);
 int zm_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy,
             uint64_t sz, int c_order, int close, int mem_kind);
 
-/* Same, for one shard of a larger volume: `origin` (voxels, logical x,y,z) is added to every
- * vertex coordinate so that shards of one volume produce identical keys on shared planes
- * (multi-GPU slab decomposition). */
-int zm_mesh_shard(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy,
-                  uint64_t sz, int c_order, int close, int mem_kind, const uint64_t origin[3]);
+/* ---- multi-GPU slab decomposition (no reference counterpart; driven by zmesh_b200/sharded.py) ----
+ * The volume is cut along its slowest memory axis (z for Fortran order, x for C order) into slabs,
+ * one handle (one GPU, one process) each.  In EXTENDED plane coordinates (input plane + 1 when
+ * close, else input plane) a shard meshes the cubes whose origin plane lies in [cube_lo, cube_hi)
+ * and therefore reads planes [cube_lo, cube_hi]; `labels` holds input planes
+ * [buf_lo, buf_lo + extent of the buffer along the slab axis).  Vertex slots are owned by voxel:
+ * the shard owns planes [cube_lo, cube_hi), plus plane cube_hi when `last`; the slots of a
+ * non-last shard's top plane belong to the next shard, so every vertex exists exactly once and
+ * per-label partial meshes concatenate without dedup.  Face indices become cross-shard indices
+ * through zm_set_label_offsets (vertices of the label on earlier shards) and the boundary-plane
+ * exchange zm_export_plane -> (NCCL send/recv) -> zm_set_foreign_plane. */
+typedef struct {
+  uint64_t full_extent;      /* voxels of the whole volume along the slab axis               */
+  uint64_t buf_lo;           /* input plane index of the buffer's first plane                */
+  uint64_t cube_lo, cube_hi; /* extended planes of the cube origins this shard owns          */
+  int last;                  /* 1 iff cube_hi is the last extended plane of the volume       */
+} zm_slab;
+int zm_mesh_slab(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy,
+                 uint64_t sz, int c_order, int close, int mem_kind, const zm_slab* slab);
+
+/* Per-label counts of the last zm_mesh / zm_mesh_slab in storage order (the order of the bulk view). */
+uint64_t zm_num_directory(zm_handle* h);
+int zm_directory(zm_handle* h, uint64_t* labels, uint64_t* n_vertices, uint64_t* n_faces, uint64_t capacity);
+
+/* offsets[i] is added to every face index of labels[i] (= number of its vertices on earlier
+ * shards).  Call after zm_mesh_slab and before the first zm_get / zm_finalize / zm_export_plane. */
+int zm_set_label_offsets(zm_handle* h, const uint64_t* labels, const uint32_t* offsets, uint64_t n);
+
+/* Writes the cross-shard indices of the in-plane vertex slots of this shard's first plane into
+ * dst_device[zm_plane_elems(h)] (uint32 [Em][Efp][4]); the shard below passes the received copy to
+ * zm_set_foreign_plane (pointer borrowed until the next zm_mesh*). */
+uint64_t zm_plane_elems(zm_handle* h);
+int zm_export_plane(zm_handle* h, uint32_t* dst_device);
+int zm_set_foreign_plane(zm_handle* h, const uint32_t* src_device);
 
 /* Replaces CMesher::ids() (cMesher.hpp:46-54).  The reference's order is unspecified
  * (unordered_map iteration); here ids are ascending.  Labels that produced no triangle are

@@ -1,0 +1,75 @@
+"""Host-side logic of the multi-GPU path on CPU: slab partition, directory all-gather (gloo,
+world_size 2) and label index offsets, part assembly."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_slab_planes_cover_every_cube_once():
+  from zmesh_b200.sharded import slab_planes
+  for full in (2, 5, 64, 513):
+    for close in (False, True):
+      pad = 1 if close else 0
+      ncube = full + 2 * pad - 1
+      for world in (1, 2, 3, 8):
+        if world > ncube:
+          with pytest.raises(ValueError):
+            slab_planes(full, close, 0, world)
+          continue
+        prev_hi = 0
+        for r in range(world):
+          lo, hi, in_lo, in_hi, last = slab_planes(full, close, r, world)
+          assert lo == prev_hi and hi > lo
+          assert in_lo == max(lo - pad, 0) and in_hi == min(hi - pad, full - 1) + 1
+          assert last == (r == world - 1)
+          prev_hi = hi
+        assert prev_hi == ncube
+
+
+def test_offsets_and_assemble():
+  from zmesh_b200.sharded import assemble, offsets_from_directories
+  ls = [np.array([5, 7, 9], np.uint64), np.array([], np.uint64), np.array([9, 7, 13], np.uint64)]
+  ns = [np.array([10, 20, 30], np.uint64), np.array([], np.uint64), np.array([4, 4, 4], np.uint64)]
+  assert offsets_from_directories(ls, ns, 0).tolist() == [0, 0, 0]
+  assert offsets_from_directories(ls, ns, 1).tolist() == []
+  assert offsets_from_directories(ls, ns, 2).tolist() == [30, 20, 0]
+  v0 = np.zeros((2, 3), np.float32); f0 = np.array([[0, 1, 2]], np.uint32)
+  v1 = np.ones((1, 3), np.float32); f1 = np.array([[2, 1, 0]], np.uint32)
+  m = assemble([(v0, f0), None, (v1, f1)])
+  assert m.vertices.shape == (3, 3) and m.faces.tolist() == [[0, 1, 2], [2, 1, 0]]
+  assert assemble([None, None]).vertices.shape == (0, 3)
+
+
+def _worker(rank, world, port, q):
+  import torch.distributed as dist
+  sys.path.insert(0, ROOT)
+  from zmesh_b200.sharded import all_gather_directories, offsets_from_directories
+  dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+  labels = [np.array([3, 2 ** 63 + 5, 8], np.uint64), np.array([8, 3], np.uint64)][rank]
+  nv = [np.array([7, 1, 2], np.uint64), np.array([5, 6], np.uint64)][rank]
+  ls, ns = all_gather_directories(labels, nv)
+  off = offsets_from_directories(ls, ns, rank)
+  q.put((rank, [l.tolist() for l in ls], off.tolist()))
+  dist.barrier()
+  dist.destroy_process_group()
+
+
+def test_directory_exchange_gloo_world2():
+  import torch.multiprocessing as mp
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 29500 + os.getpid() % 2000
+  procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = sorted(q.get(timeout=120) for _ in procs)
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  assert res[0][1] == [[3, 2 ** 63 + 5, 8], [8, 3]] and res[1][1] == res[0][1]
+  assert res[0][2] == [0, 0, 0]
+  assert res[1][2] == [2, 7]

@@ -1,0 +1,98 @@
+"""Slab sharding: N shards of one volume must assemble to exactly the
+single-shot mesh.  Here the N shards run as N handles of ONE process on one GPU (the exchange steps
+are done by hand); tests/multi_gpu_check.py runs the same thing as N processes over NCCL."""
+import numpy as np
+import pytest
+
+from oracle.oracle import OracleMesher, assert_same_mesh, random_volume, voronoi_volume
+from zmesh_b200.sharded import assemble, offsets_from_directories, slab_planes
+
+pytestmark = pytest.mark.gpu
+
+
+def run_shards(Mesher, vol, res, close, nshards):
+  import torch
+  axis = 0 if vol.flags.c_contiguous and not vol.flags.f_contiguous else 2
+  order = "C" if axis == 0 else "F"
+  full = vol.shape[axis]
+  ms, dirs, keep = [], [], []
+  for r in range(nshards):
+    cube_lo, cube_hi, in_lo, in_hi, last = slab_planes(full, close, r, nshards)
+    sl = [slice(None)] * 3
+    sl[axis] = slice(in_lo, in_hi)
+    sub = np.asarray(vol[tuple(sl)], order=order)
+    m = Mesher(res, device=0)
+    m.mesh_slab(sub, full, in_lo, cube_lo, cube_hi, last, close=close)
+    ms.append(m)
+    dirs.append(m.directory())
+  ls, ns = [d[0] for d in dirs], [d[1] for d in dirs]
+  for r, m in enumerate(ms):
+    m.set_label_offsets(ls[r], offsets_from_directories(ls, ns, r))
+  for r in range(nshards - 1, 0, -1):
+    t = torch.empty(ms[r].plane_elems(), dtype=torch.int32, device="cuda:0")
+    ms[r].export_plane(t.data_ptr())
+    ms[r].sync()
+    ms[r - 1].set_foreign_plane(t.data_ptr())
+    keep.append(t)
+  ids = sorted(set(i for m in ms for i in m.ids()))
+  out = {}
+  for lbl in ids:
+    parts = []
+    for m in ms:
+      g = m.get(lbl, normals=False, voxel_centered=True)
+      parts.append((g.vertices, g.faces) if len(g.vertices) or len(g.faces) else None)
+    out[lbl] = assemble(parts)
+  return ids, out, keep
+
+
+CASES = [
+  ("voronoi_u64_F", lambda: voronoi_volume((40, 36, 50), 12, np.uint64, 3, "F"), (4, 4, 40), False, (2, 3, 5)),
+  ("voronoi_u64_F_close", lambda: voronoi_volume((40, 36, 50), 12, np.uint64, 3, "F"), (4, 4, 40), True, (2, 4)),
+  ("random_u32_C_close", lambda: random_volume((30, 20, 33), 40, np.uint32, 7, "C"), (1, 2, 3), True, (2, 3)),
+  ("random_u16_F_thin", lambda: random_volume((34, 9, 17), 6, np.uint16, 8, "F"), (1, 1, 1), False, (2, 8)),
+  ("tile_aligned_u8_F", lambda: random_volume((64, 16, 33), 5, np.uint8, 9, "F"), (1, 1, 1), False, (2, 4)),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_shards_assemble_to_single_shot(build_all, case):
+  from zmesh_b200 import Mesher
+  name, make, res, close, shard_counts = case
+  vol = make()
+  cpu = OracleMesher(res, "port")
+  cpu.mesh(vol, close=close)
+  want_ids = sorted(cpu.ids())
+  for n in shard_counts:
+    ids, meshes, _keep = run_shards(Mesher, vol, res, close, n)
+    assert ids == want_ids, (name, n)
+    for lbl in ids:
+      assert_same_mesh(meshes[lbl], cpu.get(lbl, normals=False, voxel_centered=True), what=f"{name} n={n} label {lbl}")
+
+
+def test_slab_requires_exchange(build_all):
+  from zmesh_b200 import Mesher
+  vol = random_volume((20, 20, 20), 5, np.uint32, 1, "F")
+  cube_lo, cube_hi, in_lo, in_hi, last = slab_planes(20, False, 0, 2)
+  m = Mesher((1, 1, 1), device=0)
+  m.mesh_slab(np.asfortranarray(vol[:, :, in_lo:in_hi]), 20, in_lo, cube_lo, cube_hi, last)
+  with pytest.raises(RuntimeError, match="zm_set_foreign_plane"):
+    m.get(m.ids()[0])
+  with pytest.raises(ValueError):  # buffer does not cover the halo plane
+    m.mesh_slab(np.asfortranarray(vol[:, :, in_lo:in_hi - 1]), 20, in_lo, cube_lo, cube_hi, last)
+
+
+def test_multi_process_nccl(build_all):
+  """Real one-process-per-GPU run over NCCL (needs >= 2 GPUs: `gpurun --gpus 2`)."""
+  import os
+  import subprocess
+  import sys
+  import torch
+  n = torch.cuda.device_count()
+  if n < 2:
+    pytest.skip("needs at least 2 GPUs")
+  n = 2 if n < 4 else (4 if n < 8 else 8)
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                      "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")],
+                     capture_output=True, text=True, timeout=900)
+  assert r.returncode == 0 and "MULTI_GPU_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -52,6 +52,11 @@ class zm_bulk_view(C.Structure):
   ]
 
 
+class zm_slab(C.Structure):
+  _fields_ = [("full_extent", C.c_uint64), ("buf_lo", C.c_uint64), ("cube_lo", C.c_uint64), ("cube_hi", C.c_uint64),
+              ("last", C.c_int)]
+
+
 # every symbol include/zmesh_b200.h declares: name -> (restype, argtypes)
 _f3 = C.POINTER(C.c_float)
 _u64p = C.POINTER(C.c_uint64)
@@ -62,7 +67,13 @@ SYMBOLS = {
   "zm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
   "zm_synth_voronoi": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]),
   "zm_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]),
-  "zm_mesh_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, _u64p]),
+  "zm_mesh_slab": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(zm_slab)]),
+  "zm_num_directory": (C.c_uint64, [C.c_void_p]),
+  "zm_directory": (C.c_int, [C.c_void_p, _u64p, _u64p, _u64p, C.c_uint64]),
+  "zm_set_label_offsets": (C.c_int, [C.c_void_p, _u64p, C.POINTER(C.c_uint32), C.c_uint64]),
+  "zm_plane_elems": (C.c_uint64, [C.c_void_p]),
+  "zm_export_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
+  "zm_set_foreign_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
   "zm_num_ids": (C.c_uint64, [C.c_void_p]),
   "zm_ids": (C.c_int, [C.c_void_p, _u64p, C.c_uint64]),
   "zm_get_counts": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, _u64p]),

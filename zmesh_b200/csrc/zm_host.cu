@@ -70,6 +70,10 @@ struct zm_handle {
   DevBuf d_own6, d_rowbase, d_perm, d_vinfo, d_rec, d_tl, d_hdr, d_dense;
   // results (device)
   DevBuf d_faces, d_verts, d_normals;
+  DevBuf d_voff, d_tmpA, d_tmpB;     // slab sharding: per-table-slot index offsets; upload scratch
+  bool tl_fixed = false, have_voff = false, slab_mode = false;
+  const uint32_t* foreign = nullptr;  // borrowed: boundary-plane indices received from the next shard
+  uint64_t capL = 0;
   zm::Control* h_ctl = nullptr;  // pinned
   std::vector<uint64_t> h_list;
 
@@ -230,7 +234,7 @@ uint32_t grid_for(unsigned long long n, int block) {
 }
 
 int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz,
-             int c_order, int close, int mem_kind, const uint64_t origin[3]) {
+             int c_order, int close, int mem_kind, const zm_slab* slab) {
   if (!h) return ZM_ERR_INVALID;
   h->err.clear();
   drop_results(h);  // Mesher.mesh deletes the previous CMesher first (zmesh/_zmesh.pyx:469)
@@ -239,8 +243,12 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   if (mem_kind != ZM_MEM_HOST && mem_kind != ZM_MEM_DEVICE) return fail(h, ZM_ERR_INVALID, "bad mem_kind");
   const uint64_t pad = close ? 1 : 0;
   const uint64_t lim = (1ull << 20) - 4;
-  if (sx + origin[0] > lim || sy + origin[1] > lim || sz + origin[2] > lim)
+  if (sx > lim || sy > lim || sz > lim || (slab && slab->full_extent > lim))
     return fail(h, ZM_ERR_UNSUPPORTED, "extent exceeds the 21-bit half-voxel key range (2^20 voxels per axis)");
+  h->tl_fixed = false;
+  h->have_voff = false;
+  h->foreign = nullptr;
+  h->slab_mode = slab != nullptr;
   ZM_CUDA(h, cudaSetDevice(h->device));
   h->stats = zm_stats_t{};
   h->stats.n_voxels = sx * sy * sz;
@@ -253,10 +261,25 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   else         { vp.nf = (uint32_t)sx; vp.nm = (uint32_t)sy; vp.ns = (uint32_t)sz; }
   vp.pad = (uint32_t)pad;
   vp.Ef = vp.nf + 2 * vp.pad; vp.Em = vp.nm + 2 * vp.pad; vp.Es = vp.ns + 2 * vp.pad;
-  vp.ox = (uint32_t)origin[0]; vp.oy = (uint32_t)origin[1]; vp.oz = (uint32_t)origin[2];
+  vp.Es_own = vp.Es;
+  vp.s_shift = -(int32_t)vp.pad;
+  if (slab) {
+    // extended planes [cube_lo, cube_hi] of the whole volume; plane p is input plane p - pad
+    const uint64_t Eg = slab->full_extent + 2 * pad;
+    if (slab->cube_hi <= slab->cube_lo || slab->cube_hi > Eg - 1 || (slab->last != 0) != (slab->cube_hi == Eg - 1))
+      return fail(h, ZM_ERR_INVALID, "bad slab cube range");
+    const int64_t need_lo = std::max<int64_t>((int64_t)slab->cube_lo - (int64_t)pad, 0);
+    const int64_t need_hi = std::min<int64_t>((int64_t)slab->cube_hi - (int64_t)pad, (int64_t)slab->full_extent - 1);
+    if ((int64_t)slab->buf_lo > need_lo || (int64_t)(slab->buf_lo + vp.ns) <= need_hi)
+      return fail(h, ZM_ERR_INVALID, "slab buffer does not cover the planes its cubes need");
+    vp.Es = (uint32_t)(slab->cube_hi - slab->cube_lo + 1);
+    vp.Es_own = slab->last ? vp.Es : vp.Es - 1;
+    vp.s_shift = (int32_t)((int64_t)slab->cube_lo - (int64_t)pad - (int64_t)slab->buf_lo);
+    if (c_order) vp.ox = (uint32_t)slab->cube_lo; else vp.oz = (uint32_t)slab->cube_lo;
+  }
   // no cube without two voxels along every axis (marching_cubes.hpp:226-257 loops are empty)
   if (vp.Ef < 2 || vp.Em < 2 || vp.Es < 2) return ZM_OK;
-  vp.ntf = (vp.Ef + TF - 1) / TF; vp.ntm = (vp.Em + TM - 1) / TM; vp.nts = (vp.Es + TS - 1) / TS;
+  vp.ntf = (vp.Ef + TF - 1) / TF; vp.ntm = (vp.Em + TM - 1) / TM; vp.nts = (vp.Es_own + TS - 1) / TS;
   vp.Efp = vp.ntf * TF;
   const unsigned long long ntiles = (unsigned long long)vp.ntf * vp.ntm * vp.nts;
   if (ntiles > 0x7FFFFFFFull) return fail(h, ZM_ERR_UNSUPPORTED, "too many tiles for one launch; shard the volume");
@@ -326,9 +349,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
     ZM_CUDA(h, cudaGetLastError());
     k_scan_apply<<<cap / chunk, 1024, 0, st>>>(sa);
     ZM_CUDA(h, cudaGetLastError());
-    k_tl_fixup<<<148 * 4, 256, 0, st>>>(h->d_tl.as<TLEntry>(), d_ctl, capL, h->d_offV.as<u64>(), h->d_offT.as<u64>());
-    ZM_CUDA(h, cudaGetLastError());
-    launches += 5;
+    launches += 4;
     ZM_CUDA(h, cudaMemcpyAsync(h->h_ctl, d_ctl, sizeof(Control), cudaMemcpyDeviceToHost, st));
     ZM_CUDA(h, cudaEventRecord(h->ev[3], st));
     ZM_CUDA(h, cudaStreamSynchronize(st));
@@ -394,6 +415,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   h->vp = vp;
   h->c_order = c_order != 0;
   h->n_work = ctl.work_count;
+  h->capL = capL;
 
   h->stats.n_labels = h->sorted_ids.size();
   h->stats.n_vertices = Vtot;
@@ -417,6 +439,28 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   return ZM_OK;
 }
 
+int ensure_tl_fixed(zm_handle* h) {
+  if (h->tl_fixed || !h->n_work) return ZM_OK;
+  k_tl_fixup<<<148 * 4, 256, 0, h->stream>>>(h->d_tl.as<TLEntry>(), h->d_ctl.as<Control>(), h->capL, h->d_offV.as<u64>(),
+                                             h->d_offT.as<u64>(), h->have_voff ? h->d_voff.as<uint32_t>() : nullptr);
+  ZM_CUDA(h, cudaGetLastError());
+  h->tl_fixed = true;
+  return ZM_OK;
+}
+
+Pass2Args pass2_args(zm_handle* h) {
+  Pass2Args a{};
+  a.hdr = h->d_hdr.as<TileHdr>();
+  a.own6 = h->d_own6.as<uint8_t>();
+  a.rowbase = h->d_rowbase.as<uint32_t>();
+  a.perm = h->d_perm.as<uint32_t>();
+  a.vinfo = h->d_vinfo.as<uint32_t>();
+  a.rec = h->d_rec.as<uint32_t>();
+  a.tl = h->d_tl.as<TLEntry>();
+  a.foreign = h->foreign;
+  return a;
+}
+
 // Pass 2 (lazy): faces once per zm_mesh; vertices per (voxel_centered, transpose, offset); normals per
 // transpose.  Everything is written in its final layout on the device.
 int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, const float* off) {
@@ -436,20 +480,19 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
   ZM_CUDA(h, cudaEventRecord(h->ev[5], st));
   ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
   if (h->Vtot && h->n_work) {
+    if (h->vp.Es_own < h->vp.Es && !h->foreign)
+      return fail(h, ZM_ERR_STATE, "slab shard: zm_set_foreign_plane must be called before the first get/finalize");
+    if (normals && h->slab_mode)
+      return fail(h, ZM_ERR_UNSUPPORTED, "normals are not available for slab shards yet");
+    int rc = ensure_tl_fixed(h);
+    if (rc != ZM_OK) return rc;
     ZM_CUDA(h, h->d_faces.ensure((size_t)h->Ttot * 12));
     ZM_CUDA(h, h->d_verts.ensure((size_t)h->Vtot * 12));
     if (need_normals) {
       ZM_CUDA(h, h->d_normals.ensure((size_t)h->Vtot * 12));
       ZM_CUDA(h, cudaMemsetAsync(h->d_normals.p, 0, (size_t)h->Vtot * 12, st));
     }
-    Pass2Args a{};
-    a.hdr = h->d_hdr.as<TileHdr>();
-    a.own6 = h->d_own6.as<uint8_t>();
-    a.rowbase = h->d_rowbase.as<uint32_t>();
-    a.perm = h->d_perm.as<uint32_t>();
-    a.vinfo = h->d_vinfo.as<uint32_t>();
-    a.rec = h->d_rec.as<uint32_t>();
-    a.tl = h->d_tl.as<TLEntry>();
+    Pass2Args a = pass2_args(h);
     a.faces = h->d_faces.as<uint32_t>();
     a.verts = h->d_verts.as<float>();
     a.normals = h->d_normals.as<float>();
@@ -541,7 +584,7 @@ void zm_destroy(zm_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_vol, &h->d_keys, &h->d_cnt, &h->d_offV, &h->d_offT, &h->d_list, &h->d_partial, &h->d_ctl,
                     &h->d_own6, &h->d_rowbase, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_hdr,
-                    &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals})
+                    &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals, &h->d_voff, &h->d_tmpA, &h->d_tmpB})
     b->release();
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   for (auto& ev : h->ev)
@@ -591,14 +634,72 @@ int zm_set_resolution(zm_handle* h, const float resolution[3]) {
 
 int zm_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz,
             int c_order, int close, int mem_kind) {
-  const uint64_t origin[3] = {0, 0, 0};
-  return run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, origin);
+  return run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, nullptr);
 }
 
-int zm_mesh_shard(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz,
-                  int c_order, int close, int mem_kind, const uint64_t origin[3]) {
-  if (!origin) return ZM_ERR_INVALID;
-  return run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, origin);
+int zm_mesh_slab(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz,
+                 int c_order, int close, int mem_kind, const zm_slab* slab) {
+  if (!slab) return ZM_ERR_INVALID;
+  return run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, slab);
+}
+
+int zm_directory(zm_handle* h, uint64_t* labels, uint64_t* n_vertices, uint64_t* n_faces, uint64_t capacity) {
+  if (!h) return ZM_ERR_INVALID;
+  const uint64_t n = std::min<uint64_t>(capacity, h->recs.size());
+  for (uint64_t i = 0; i < n; ++i) {
+    if (labels) labels[i] = h->recs[i].label;
+    if (n_vertices) n_vertices[i] = h->recs[i].nv;
+    if (n_faces) n_faces[i] = h->recs[i].nt;
+  }
+  return ZM_OK;
+}
+
+uint64_t zm_num_directory(zm_handle* h) { return h ? h->recs.size() : 0; }
+
+int zm_set_label_offsets(zm_handle* h, const uint64_t* labels, const uint32_t* offsets, uint64_t n) {
+  if (!h || (n && (!labels || !offsets))) return ZM_ERR_INVALID;
+  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  if (h->tl_fixed) return fail(h, ZM_ERR_STATE, "label offsets must be set before the first get/finalize/export");
+  if (!h->n_work) return ZM_OK;
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  const uint32_t cap = h->hash_cap;
+  ZM_CUDA(h, h->d_voff.ensure((size_t)cap * 4));
+  ZM_CUDA(h, cudaMemsetAsync(h->d_voff.p, 0, (size_t)cap * 4, h->stream));
+  if (n) {
+    ZM_CUDA(h, h->d_tmpA.ensure(n * 8));
+    ZM_CUDA(h, h->d_tmpB.ensure(n * 4));
+    ZM_CUDA(h, cudaMemcpyAsync(h->d_tmpA.p, labels, n * 8, cudaMemcpyHostToDevice, h->stream));
+    ZM_CUDA(h, cudaMemcpyAsync(h->d_tmpB.p, offsets, n * 4, cudaMemcpyHostToDevice, h->stream));
+    LabelTable ht{h->d_keys.as<u64>(), h->d_cnt.as<u64>(), cap - 1};
+    k_set_voff<<<grid_for(n, 256), 256, 0, h->stream>>>(ht, h->d_tmpA.as<u64>(), h->d_tmpB.as<uint32_t>(), n,
+                                                        h->d_voff.as<uint32_t>());
+    ZM_CUDA(h, cudaGetLastError());
+    ZM_CUDA(h, cudaStreamSynchronize(h->stream));  // the host arrays are borrowed
+  }
+  h->have_voff = true;
+  return ZM_OK;
+}
+
+uint64_t zm_plane_elems(zm_handle* h) { return h ? 4ull * h->vp.Em * h->vp.Efp : 0; }
+
+int zm_export_plane(zm_handle* h, uint32_t* dst_device) {
+  if (!h || !dst_device) return ZM_ERR_INVALID;
+  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  if (!h->n_work) return ZM_OK;
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_tl_fixed(h);
+  if (rc != ZM_OK) return rc;
+  Pass2Args a = pass2_args(h);
+  if (h->c_order) k_export_plane<true><<<h->n_work, NT_V, 0, h->stream>>>(h->vp, a, dst_device);
+  else k_export_plane<false><<<h->n_work, NT_V, 0, h->stream>>>(h->vp, a, dst_device);
+  ZM_CUDA(h, cudaGetLastError());
+  return ZM_OK;
+}
+
+int zm_set_foreign_plane(zm_handle* h, const uint32_t* src_device) {
+  if (!h) return ZM_ERR_INVALID;
+  h->foreign = src_device;
+  return ZM_OK;
 }
 
 uint64_t zm_num_ids(zm_handle* h) { return h ? h->sorted_ids.size() : 0; }

@@ -75,6 +75,11 @@ struct VolParams {
   uint32_t ntf, ntm, nts;  // tiles per axis
   uint32_t ox, oy, oz;     // shard origin in logical voxels (added to keys)
   uint32_t use_tma;
+  // slab sharding along s (multi-GPU): planes [0, Es_own) own vertex slots; when Es_own == Es - 1
+  // the top plane belongs to the next shard and is only read as cube corners.  s_shift maps an
+  // extended local plane to a plane of the buffer (-pad for an unsharded volume).
+  uint32_t Es_own;
+  int32_t s_shift;
 };
 
 struct LabelTable {  // global open-addressing table, key 0 = empty (label 0 is never meshed)
@@ -92,9 +97,9 @@ struct __align__(16) TileHdr {  // one per non-empty tile, in work-list order
 };
 static_assert(sizeof(TileHdr) == 32, "TileHdr is loaded as two 16-byte words");
 
-struct __align__(16) TLEntry {  // pass 1: a = label slot | face base in label << 32;  final: a = first
-  u64 a, b;                     // vertex row of the label, b = first face row of this (tile,label)
-};
+struct __align__(16) TLEntry {  // pass 1: a = label slot | face base in label << 32;  after k_tl_fixup:
+  u64 a, b;                     // a = first vertex row of the label | index offset of the label << 32
+};                              // (vertices of the label on earlier shards), b = first face row of this (tile,label)
 
 // control block (device): cursors and flags
 struct Control {
@@ -297,7 +302,7 @@ __device__ __forceinline__ void scan_tile(const VolParams& vp, const Pass1Args& 
   const int lane = threadIdx.x & 31, ls = threadIdx.x >> 5;
   const uint32_t ltm = (1u << lane) - 1u;
   const uint32_t ef = ef0 + lane, es = es0 + ls;
-  const bool okf = INTERIOR || ef < vp.Ef, oks = INTERIOR || es < vp.Es;
+  const bool okf = INTERIOR || ef < vp.Ef, oks = INTERIOR || es < vp.Es_own;
   const bool nf1 = INTERIOR || ef + 1 < vp.Ef, ns1 = INTERIOR || es + 1 < vp.Es;
   const L* p = lab + (ls * RM) * RFP + lane;
   L a = p[0], af = p[1], as_ = p[RM * RFP];
@@ -377,7 +382,7 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
     if (tid == 0) {
       fence_proxy_async();
       mbar_expect_tx(&S.mbar, (uint32_t)(sizeof(L) * RS * RM * RFP));
-      tma_load_3d(S.lab, tmap, &S.mbar, (int)ef0 - (vp.pad ? ALIGN : 0), (int)em0 - (int)vp.pad, (int)es0 - (int)vp.pad);
+      tma_load_3d(S.lab, tmap, &S.mbar, (int)ef0 - (vp.pad ? ALIGN : 0), (int)em0 - (int)vp.pad, (int)es0 + vp.s_shift);
     }
   } else {
     const L* __restrict__ src = static_cast<const L*>(vp.data);
@@ -385,7 +390,7 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
       const int lf = i % (TF + 1);
       const int t = i / (TF + 1);
       const int lm = t % RM, ls = t / RM;
-      const uint32_t jf = ef0 + lf - vp.pad, jm = em0 + lm - vp.pad, js = es0 + ls - vp.pad;  // wraps when < 0
+      const uint32_t jf = ef0 + lf - vp.pad, jm = em0 + lm - vp.pad, js = es0 + ls + (uint32_t)vp.s_shift;  // wraps when < 0
       L v = 0;
       if (jf < vp.nf && jm < vp.nm && js < vp.ns) v = src[((size_t)js * vp.nm + jm) * vp.nf + jf];
       lab[(ls * RM + lm) * RFP + lf] = v;
@@ -576,7 +581,7 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
   if (tid == 0 && S.ttot) atomicAdd(&o.ctl->cur_tri, (u64)S.ttot);
   if (tid < TM * TS) {
     const uint32_t rs = es0 + tid / TM, rm = em0 + tid % TM;
-    if (rs < vp.Es && rm < vp.Em) o.rowbase[((size_t)rs * vp.Em + rm) * vp.ntf + tf] = gbase + S.rowpre[tid];
+    if (rs < vp.Es_own && rm < vp.Em) o.rowbase[((size_t)rs * vp.Em + rm) * vp.ntf + tf] = gbase + S.rowpre[tid];
   }
   for (uint32_t i = tid; i < nslots; i += NT) {
     const uint32_t w = S.vstage[i];
@@ -726,19 +731,35 @@ __global__ void __launch_bounds__(1024) k_scan_apply(const ScanArgs a) {
   }
 }
 
-// tl[i]: (label slot | face base in label << 32)  ->  (first vertex row of the label, first face row of the
-// (tile,label) block)
+// tl[i]: (label slot | face base in label << 32)  ->  (first vertex row of the label | shard index offset << 32,
+// first face row of the (tile,label) block)
 __global__ void __launch_bounds__(256) k_tl_fixup(TLEntry* tl, const Control* ctl, u64 capL, const u64* offV,
-                                                  const u64* offT) {
+                                                  const u64* offT, const uint32_t* voff) {
   u64 n = ctl->cur_tl;
   if (n > capL) n = capL;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
     const u64 a = tl[i].a;
     const uint32_t gs = (uint32_t)a;
     TLEntry e;
-    e.a = offV[gs];
+    e.a = offV[gs] | ((u64)(voff ? voff[gs] : 0u) << 32);
     e.b = offT[gs] + (a >> 32);
     tl[i] = e;
+  }
+}
+
+// voff[slot(labels[i])] = offs[i]  (labels absent from the table are ignored)
+__global__ void __launch_bounds__(256) k_set_voff(const LabelTable ht, const u64* labels, const uint32_t* offs, u64 n,
+                                                  uint32_t* voff) {
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 label = labels[i];
+    if (label == 0ull) continue;
+    uint32_t h = hash_label(label) & ht.mask;
+    for (uint32_t p = 0; p <= ht.mask && p < 4096u; ++p) {
+      const u64 k = ht.keys[h];
+      if (k == label) { voff[h] = offs[i]; break; }
+      if (k == 0ull) break;
+      h = (h + 1u) & ht.mask;
+    }
   }
 }
 
@@ -760,6 +781,7 @@ struct Pass2Args {
   float c0, c1, c2;  // centering offset
   int voxel_centered, transpose;
   int write_faces, write_verts, normalize;
+  const uint32_t* foreign;  // slab sharding: final indices of the top plane's slots, [Em][Efp][4], from the next shard
 };
 
 __device__ __forceinline__ float len3(float x, float y, float z) {
@@ -879,6 +901,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
   __shared__ u64 rf[NW][32];              // per record of the warp's batch: first face row
   __shared__ u64 rv[NW][32];              //                                  first vertex row of the label
   __shared__ uint32_t ru[NW][32];         //                                  region index | case << 16
+  __shared__ uint32_t rvo[NW][32];        //                                  index offset of the label (earlier shards)
   __shared__ uint8_t tlist[NW][160];      // triangles of the batch: record lane << 3 | t
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -911,7 +934,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
       const int r = warp + NW * (half * HB + i);
       const int ls = r / RM, lm = r - ls * RM;
       const uint32_t em = em0 + lm, es = es0 + ls;
-      const bool rowvalid = r < NROW && em < vp.Em && es < vp.Es;
+      const bool rowvalid = r < NROW && em < vp.Em && es < vp.Es_own;
       const size_t row = (size_t)es * vp.Em + em;
       mrow[i] = rowvalid ? a.own6[row * vp.Efp + ef0 + lane] : 0u;
       rbrow[i] = rowvalid ? __ldg(a.rowbase + row * vp.ntf + tf) : 0u;
@@ -925,11 +948,20 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
         const uint32_t m = mrow[i];
         uint32_t pre = 0, rowtotal;
         if (__ballot_sync(FULL, m != 0u)) pre = warp_prefix3(__popc(m), ltm, rowtotal);
-        o6[r * FW + lane] = (uint8_t)m;
-        gb[r * FW + lane] = rbrow[i] + pre;
-        if (lane == 0) {
-          o6[r * FW + TF] = (uint8_t)mh[i];
-          gb[r * FW + TF] = rbh[i];
+        const int ls = r / RM, lm = r - ls * RM;
+        if (es0 + ls == vp.Es_own && vp.Es_own < vp.Es) {
+          // top plane of a slab: its slots belong to the next shard; look them up in a.foreign
+          const uint32_t fbase = 0x80000000u | ((em0 + lm) * vp.Efp + ef0);
+          o6[r * FW + lane] = 0;
+          gb[r * FW + lane] = fbase + lane;
+          if (lane == 0) { o6[r * FW + TF] = 0; gb[r * FW + TF] = fbase + TF; }
+        } else {
+          o6[r * FW + lane] = (uint8_t)m;
+          gb[r * FW + lane] = rbrow[i] + pre;
+          if (lane == 0) {
+            o6[r * FW + TF] = (uint8_t)mh[i];
+            gb[r * FW + TF] = rbh[i];
+          }
         }
       }
     }
@@ -959,7 +991,8 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
       const uint32_t lf = vidx & 31u, lm = (vidx >> 5) & 7u, ls = vidx >> 8;
       ru[warp][lane] = ((ls * RM + lm) * FW + lf) | (cs << 16);
       rf[warp][lane] = e.b + old + pre;
-      if (NORMALS) rv[warp][lane] = e.a;
+      rvo[warp][lane] = (uint32_t)(e.a >> 32);
+      if (NORMALS) rv[warp][lane] = e.a & 0xFFFFFFFFull;
       for (uint32_t t = 0; t < nt; ++t) tlist[warp][tpre + t] = (uint8_t)((lane << 3) | t);
     }
     __syncwarp();
@@ -975,8 +1008,10 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
       const uint32_t u = u0 + (en & 0x1FFu);
       // slot = 2*axis + side; side 0: the owner (lower) voxel carries the label, 1: the upper one
       const uint32_t slot = (en >> 9) & 7u;
-      const uint32_t g = gb[u] + __popc((uint32_t)o6[u] & ((1u << slot) - 1u));
-      const uint32_t vi = __ldg(a.perm + g);
+      const uint32_t gv = gb[u];
+      uint32_t vi;
+      if (gv & 0x80000000u) vi = __ldg(a.foreign + 4ull * (gv & 0x7FFFFFFFu) + slot);
+      else vi = __ldg(a.perm + gv + __popc((uint32_t)o6[u] & ((1u << slot) - 1u))) + rvo[warp][src];
       if (a.write_faces) a.faces[3ull * (rf[warp][src] + t) + k] = vi;
       if (NORMALS) {
         // the lane owning corner k recomputes the face normal from the cube geometry (no loads)
@@ -988,7 +1023,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
           slot_position<CO>(vp, a, ef0 + lf + ((ec >> 12) & 1u), em0 + lm + ((ec >> 13) & 1u),
                             es0 + ls + ((ec >> 14) & 1u), ((ec >> 9) & 7u) >> 1, p[c][0], p[c][1], p[c][2]);
         }
-        float* dst = a.normals + 3ull * (rv[warp][src] + vi);
+        float* dst = a.normals + 3ull * (rv[warp][src] + vi - rvo[warp][src]);
         // legacy faces (t0,t2,t1) = the stored row reversed: corner k becomes corner 2-k
         if (a.transpose) face_normal_corner(p[2], p[1], p[0], 2 - (int)k, dst);
         else face_normal_corner(p[0], p[1], p[2], (int)k, dst);
@@ -1016,7 +1051,7 @@ __global__ void __launch_bounds__(NT_V) k_vertices(const VolParams vp, const Pas
     const uint32_t rank = __ldg(a.perm + h.gbase + i);
     const uint32_t w = __ldg(a.vinfo + h.gbase + i);
     const uint32_t vidx = w & 0x7FFu, s6 = (w >> 11) & 7u, ci = w >> 14;
-    const u64 dst = tl[ci].a + rank;
+    const u64 dst = (tl[ci].a & 0xFFFFFFFFull) + rank;
     if (a.write_verts) {
       float p0, p1, p2;
       slot_position<CO>(vp, a, ef0 + (vidx & 31u), em0 + ((vidx >> 5) & 7u), es0 + (vidx >> 8), s6 >> 1, p0, p1, p2);
@@ -1033,6 +1068,26 @@ __global__ void __launch_bounds__(NT_V) k_vertices(const VolParams vp, const Pas
       if (l != 1.0f) { x = __fdiv_rn(x, l); y = __fdiv_rn(y, l); z = __fdiv_rn(z, l); }  // 0/0 -> NaN like hat()
       nn[0] = x; nn[1] = y; nn[2] = z;
     }
+  }
+}
+
+// slab sharding: final (cross-shard) indices of the in-plane slots of this shard's FIRST plane, for
+// the shard below whose cubes reference them: dst[(em * Efp + ef) * 4 + slot] = label offset + rank
+template <bool CO>
+__global__ void __launch_bounds__(NT_V) k_export_plane(const VolParams vp, const Pass2Args a, uint32_t* dst) {
+  const TileHdr h = load_hdr(a.hdr + blockIdx.x);
+  uint32_t b = h.tile;
+  const uint32_t tf = b % vp.ntf;
+  b /= vp.ntf;
+  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
+  if (ts != 0 || h.nslots == 0) return;
+  const TLEntry* tl = a.tl + h.tlbase;
+  for (uint32_t i = threadIdx.x; i < h.nslots; i += NT_V) {
+    const uint32_t w = __ldg(a.vinfo + h.gbase + i);
+    const uint32_t vidx = w & 0x7FFu, s6 = (w >> 11) & 7u, ci = w >> 14;
+    if ((vidx >> 8) != 0u || s6 >= 4u) continue;
+    const uint32_t ef = tf * TF + (vidx & 31u), em = tm * TM + ((vidx >> 5) & 7u);
+    dst[4ull * ((size_t)em * vp.Efp + ef) + s6] = (uint32_t)(tl[ci].a >> 32) + __ldg(a.perm + h.gbase + i);
   }
 }
 

@@ -114,23 +114,48 @@ class Mesher:
     self._max_label = (1 << (8 * nbytes)) - 1
     self._check(self._call_mesh(data.ctypes.data, nbytes, shape, c_order, close, 0))
 
-  def mesh_shard(self, data, origin, close: bool = False):
-    """Mesh one shard of a larger volume: like mesh(), but `origin` (x, y, z voxels) is added to
-    every vertex coordinate so that neighbouring shards agree on the keys of shared planes."""
-    self._origin = tuple(int(o) for o in origin)
+  def _call_mesh(self, ptr, nbytes, shape, c_order, close, mem_kind):
+    slab = getattr(self, "_slab", None)
+    if slab is None:
+      return self._lib.zm_mesh(self._h, C.c_void_p(ptr), nbytes, shape[0], shape[1], shape[2], c_order,
+                               1 if close else 0, mem_kind)
+    return self._lib.zm_mesh_slab(self._h, C.c_void_p(ptr), nbytes, shape[0], shape[1], shape[2], c_order,
+                                  1 if close else 0, mem_kind, C.byref(slab))
+
+  # -- multi-GPU slab pieces (driven by zmesh_b200.sharded.ShardedMesher) ----------------------------
+  def mesh_slab(self, data, full_extent, buf_lo, cube_lo, cube_hi, last, close: bool = False):
+    """Mesh one slab of a larger volume (see zm_mesh_slab in include/zmesh_b200.h): `data` holds the
+    input planes [buf_lo, buf_lo + n) along the slowest memory axis; the shard owns the cubes whose
+    origin (extended coordinates) lies in [cube_lo, cube_hi)."""
+    self._slab = _lib.zm_slab(int(full_extent), int(buf_lo), int(cube_lo), int(cube_hi), 1 if last else 0)
     try:
       return self.mesh(data, close=close)
     finally:
-      self._origin = None
+      self._slab = None
 
-  def _call_mesh(self, ptr, nbytes, shape, c_order, close, mem_kind):
-    origin = getattr(self, "_origin", None)
-    if origin is None:
-      return self._lib.zm_mesh(self._h, C.c_void_p(ptr), nbytes, shape[0], shape[1], shape[2], c_order,
-                               1 if close else 0, mem_kind)
-    o = (C.c_uint64 * 3)(*origin)
-    return self._lib.zm_mesh_shard(self._h, C.c_void_p(ptr), nbytes, shape[0], shape[1], shape[2], c_order,
-                                   1 if close else 0, mem_kind, o)
+  def directory(self):
+    """(labels, n_vertices, n_faces) of the last mesh call, storage order (uint64 arrays)."""
+    n = int(self._lib.zm_num_directory(self._h))
+    out = [np.empty(n, dtype=np.uint64) for _ in range(3)]
+    if n:
+      p = [o.ctypes.data_as(C.POINTER(C.c_uint64)) for o in out]
+      self._check(self._lib.zm_directory(self._h, p[0], p[1], p[2], n))
+    return tuple(out)
+
+  def set_label_offsets(self, labels, offsets):
+    labels = np.ascontiguousarray(labels, dtype=np.uint64)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+    self._check(self._lib.zm_set_label_offsets(self._h, labels.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               offsets.ctypes.data_as(C.POINTER(C.c_uint32)), labels.size))
+
+  def plane_elems(self) -> int:
+    return int(self._lib.zm_plane_elems(self._h))
+
+  def export_plane(self, dst_device_ptr: int):
+    self._check(self._lib.zm_export_plane(self._h, C.c_void_p(int(dst_device_ptr))))
+
+  def set_foreign_plane(self, src_device_ptr):
+    self._check(self._lib.zm_set_foreign_plane(self._h, C.c_void_p(int(src_device_ptr)) if src_device_ptr else None))
 
   def set_stream(self, cuda_stream):
     """Queue all work on a caller-owned CUDA stream (integer cudaStream_t); None restores the own one."""

@@ -1,0 +1,178 @@
+"""Multi-GPU slab sharding of the mesh+get path: one process per GPU (torch.distributed, NCCL over
+NVLink), no reference counterpart (the reference is a single-threaded CPU library).
+
+Sharding.  The volume is cut along its slowest memory axis (z for Fortran order, x for C order)
+into `world` slabs of cube-origin planes; rank r reads its planes plus ONE halo plane on the high
+side.  Every cube belongs to exactly one rank, so triangles are never duplicated.  Vertices are
+owned by voxel (a vertex is a grid edge, owned by its lower voxel): the halo plane's slots belong
+to rank r+1, so every vertex exists exactly once across ranks as well -- per-label partial meshes
+CONCATENATE, there is nothing to dedup.  What has to be exchanged is only bookkeeping:
+
+  1. all-gather of every rank's (label, n_vertices) directory -> rank r's face indices of label L
+     are shifted by the number of L's vertices on ranks < r (`label_offsets`);
+  2. rank r+1 sends rank r the final indices of the vertex slots in the shared plane
+     (uint32 [Em][Efp][4], one NCCL send/recv between neighbours), which rank r's face kernel
+     reads for the corners of its top cube layer.
+
+The result stays distributed: rank r holds, for every label, the vertices it owns and the faces of
+its cubes with global (cross-rank) indices; `gather_mesh(label)` concatenates the parts in rank
+order, which is bit-identical (as canonical sets) to the single-GPU mesh.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .mesh import Mesh
+from .mesher import Mesher
+
+
+def slab_planes(full_extent: int, close: bool, rank: int, world: int):
+  """Cube-origin planes [cube_lo, cube_hi) of `rank` in EXTENDED coordinates (input plane + 1 when
+  close) and the input planes [in_lo, in_hi) it has to read.  Returns (cube_lo, cube_hi, in_lo, in_hi, last)."""
+  pad = 1 if close else 0
+  ncube = full_extent + 2 * pad - 1  # cube-origin planes of the whole (extended) volume
+  if world > ncube:
+    raise ValueError("more ranks than cube planes")
+  cube_lo = (ncube * rank) // world
+  cube_hi = (ncube * (rank + 1)) // world
+  in_lo = max(cube_lo - pad, 0)
+  in_hi = min(cube_hi - pad, full_extent - 1) + 1
+  return cube_lo, cube_hi, in_lo, in_hi, rank == world - 1
+
+
+def offsets_from_directories(labels_by_rank, nv_by_rank, rank: int):
+  """Index offset of each of rank's labels = its vertices on earlier ranks (pure numpy)."""
+  mine = np.asarray(labels_by_rank[rank], dtype=np.uint64)
+  if rank == 0 or mine.size == 0:
+    return np.zeros(mine.size, dtype=np.uint32)
+  prev_l = np.concatenate([np.asarray(labels_by_rank[q], dtype=np.uint64) for q in range(rank)])
+  prev_n = np.concatenate([np.asarray(nv_by_rank[q], dtype=np.uint64) for q in range(rank)])
+  if prev_l.size == 0:
+    return np.zeros(mine.size, dtype=np.uint32)
+  uniq, inv = np.unique(prev_l, return_inverse=True)
+  tot = np.zeros(uniq.size, dtype=np.uint64)
+  np.add.at(tot, inv, prev_n)
+  pos = np.searchsorted(uniq, mine)
+  pos_c = np.minimum(pos, uniq.size - 1)
+  hit = uniq[pos_c] == mine
+  out = np.where(hit, tot[pos_c], 0)
+  if out.size and int(out.max()) >= 2 ** 32:
+    raise ValueError("a label has more than 2^32-1 vertices")
+  return out.astype(np.uint32)
+
+
+def all_gather_directories(labels, nv, group=None, device=None):
+  """All-gather of variable-length (label, count) directories; works with gloo (CPU) and NCCL."""
+  import torch
+  import torch.distributed as dist
+  world = dist.get_world_size(group)
+  dev = device if device is not None else "cpu"
+  n = torch.tensor([labels.size], dtype=torch.int64, device=dev)
+  sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+  dist.all_gather(sizes, n, group=group)
+  sizes = [int(s.item()) for s in sizes]
+  m = max(max(sizes), 1)
+  buf = torch.zeros((m, 2), dtype=torch.int64, device=dev)
+  if labels.size:
+    both = np.stack([labels.astype(np.uint64).view(np.int64), nv.astype(np.uint64).view(np.int64)], axis=1)
+    buf[:labels.size] = torch.from_numpy(both).to(dev)
+  outs = [torch.zeros_like(buf) for _ in range(world)]
+  dist.all_gather(outs, buf, group=group)
+  ls, ns = [], []
+  for q in range(world):
+    a = outs[q][:sizes[q]].cpu().numpy()
+    ls.append(a[:, 0].copy().view(np.uint64))
+    ns.append(a[:, 1].copy().view(np.uint64))
+  return ls, ns
+
+
+def assemble(parts):
+  """Concatenate per-rank parts [(vertices, faces) or None, ...] in rank order -> Mesh."""
+  vs = [p[0] for p in parts if p is not None and len(p[0])]
+  fs = [p[1] for p in parts if p is not None and len(p[1])]
+  v = np.concatenate(vs) if vs else np.zeros((0, 3), np.float32)
+  f = np.concatenate(fs) if fs else np.zeros((0, 3), np.uint32)
+  return Mesh(v, f, None)
+
+
+class ShardedMesher:
+  """One instance per rank.  mesh_slab() runs the rank's share of the path and the exchanges;
+  afterwards the rank holds its parts of every label (device resident until fetched)."""
+
+  def __init__(self, voxel_res, device: int, group=None):
+    import torch.distributed as dist
+    self.group = group
+    self.rank = dist.get_rank(group)
+    self.world = dist.get_world_size(group)
+    self.device = int(device)
+    self.mesher = Mesher(voxel_res, device=self.device)
+    self._plane_send = None
+    self._plane_recv = None
+    self._dir = None
+
+  def planes(self, full_extent: int, close: bool = False):
+    return slab_planes(int(full_extent), bool(close), self.rank, self.world)
+
+  def mesh_slab(self, data, full_extent: int, buf_lo: int, close: bool = False, finalize: bool = True,
+                voxel_centered: bool = False):
+    """data: this rank's planes [buf_lo, buf_lo + n) of the volume along the slab axis (numpy array or
+    CUDA tensor), covering at least planes(full_extent, close)[2:4]."""
+    import torch
+    import torch.distributed as dist
+    cube_lo, cube_hi, in_lo, in_hi, last = self.planes(full_extent, close)
+    m = self.mesher
+    m.mesh_slab(data, full_extent, buf_lo, cube_lo, cube_hi, last, close=close)
+    labels, nv, nt = m.directory()
+    dev = f"cuda:{self.device}"
+    ls, ns = all_gather_directories(labels, nv, self.group, dev)
+    m.set_label_offsets(labels, offsets_from_directories(ls, ns, self.rank))
+    self._dir = (labels, nv, nt)
+    # boundary plane: rank r+1 -> rank r
+    n = m.plane_elems()
+    ops = []
+    stream = torch.cuda.current_stream()
+    if self.rank > 0:
+      if self._plane_send is None or self._plane_send.numel() != n:
+        self._plane_send = torch.empty(n, dtype=torch.int32, device=dev)
+      m.export_plane(self._plane_send.data_ptr())
+      m.sync()
+      ops.append(dist.P2POp(dist.isend, self._plane_send, self.rank - 1, group=self.group))
+    if not last:
+      if self._plane_recv is None or self._plane_recv.numel() != n:
+        self._plane_recv = torch.empty(n, dtype=torch.int32, device=dev)
+      ops.append(dist.P2POp(dist.irecv, self._plane_recv, self.rank + 1, group=self.group))
+    if ops:
+      for w in dist.batch_isend_irecv(ops):
+        w.wait()
+      stream.synchronize()
+    m.set_foreign_plane(self._plane_recv.data_ptr() if not last else None)
+    if finalize:
+      return m.finalize(normals=False, voxel_centered=voxel_centered)
+    return None
+
+  def local_part(self, label, voxel_centered: bool = False):
+    """(vertices, faces) this rank holds for `label` (faces carry cross-rank indices) or None."""
+    mesh = self.mesher.get(label, normals=False, voxel_centered=voxel_centered)
+    if len(mesh.vertices) == 0 and len(mesh.faces) == 0:
+      return None
+    return mesh.vertices, mesh.faces
+
+  def all_ids(self):
+    """Sorted ids of the whole volume (every rank gets the same list)."""
+    import torch.distributed as dist
+    mine = self.mesher.ids()
+    outs = [None] * self.world
+    dist.all_gather_object(outs, mine, group=self.group)
+    return sorted(set(i for o in outs for i in o))
+
+  def gather_mesh(self, label, dst: int = 0, voxel_centered: bool = False):
+    """Assemble the full mesh of `label` on rank `dst` (None elsewhere)."""
+    import torch.distributed as dist
+    part = self.local_part(label, voxel_centered)
+    outs = [None] * self.world if self.rank == dst else None
+    dist.gather_object(part, outs, dst=dst, group=self.group)
+    if self.rank != dst:
+      return None
+    mesh = assemble(outs)
+    mesh.id = int(label)
+    return mesh
