@@ -158,6 +158,10 @@ int zm_finalize(zm_handle* h, int normals, int voxel_centered, int transpose,
  * (vertices 3*V_total floats, faces 3*T_total uint32, normals 3*V_total floats or NULL). */
 int zm_fetch_all(zm_handle* h, float* vertices, uint32_t* faces, float* normals_out);
 
+/* Page-locked host memory for zm_fetch_all destinations (full-speed D2H); NULL on failure. */
+void* zm_host_alloc(uint64_t bytes);
+void zm_host_free(void* p);
+
 typedef struct {
   uint64_t n_voxels, n_labels, n_vertices, n_faces;
   uint64_t n_records;      /* (label, cube) pairs that produced triangles                          */

@@ -83,6 +83,8 @@ SYMBOLS = {
   "zm_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f3, C.POINTER(zm_bulk_view)]),
   "zm_fetch_all": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
   "zm_compute_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]),
+  "zm_host_alloc": (C.c_void_p, [C.c_uint64]),
+  "zm_host_free": (None, [C.c_void_p]),
   "zm_stats": (C.c_int, [C.c_void_p, C.POINTER(zm_stats_t)]),
   "zm_sync": (C.c_int, [C.c_void_p]),
   "zm_last_error": (C.c_char_p, [C.c_void_p]),

@@ -852,6 +852,19 @@ int zm_compute_normals(zm_handle* h, const float* vertices, uint64_t n_vertices,
   return rc;
 }
 
+void* zm_host_alloc(uint64_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void zm_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int zm_stats(zm_handle* h, zm_stats_t* out) {
   if (!h || !out) return ZM_ERR_INVALID;
   *out = h->stats;

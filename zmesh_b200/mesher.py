@@ -18,6 +18,7 @@ NotImplementedError; there is no CPU fallback for anything.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -34,6 +35,41 @@ def _f3(a):
   return a
 
 
+class _PinnedBlock:
+  """Page-locked host block the bulk device-to-host copy lands in; arrays handed to the user are views
+  of it and keep it alive (the ctypes buffer they are based on references the block)."""
+
+  def __init__(self, lib, nbytes: int):
+    self._lib = lib
+    self.nbytes = max(int(nbytes), 1)
+    self.ptr = lib.zm_host_alloc(self.nbytes)
+    if not self.ptr:
+      raise MemoryError(f"zmesh_b200: cannot allocate {self.nbytes} bytes of pinned host memory")
+    self._buf = (C.c_ubyte * self.nbytes).from_address(self.ptr)
+    self._buf._zm_owner = self  # arrays -> ctypes buffer -> block
+    self._live = []
+
+  def view(self, dtype, shape, offset: int) -> np.ndarray:
+    root = np.frombuffer(self._buf, dtype=dtype, count=int(np.prod(shape)), offset=offset)
+    self._live.append(weakref.ref(root))  # every view/slice handed out has `root` as its base
+    return root.reshape(shape)
+
+  def idle(self) -> bool:
+    self._live = [r for r in self._live if r() is not None]
+    return not self._live
+
+  def __del__(self):
+    try:
+      self._lib.zm_host_free(self.ptr)
+    except Exception:
+      pass
+
+
+class _Stage:
+  """All labels' final arrays on the host (one bulk transfer), sliced per label by get()."""
+  __slots__ = ("key", "v", "f", "n", "index", "given")
+
+
 class Mesher:
   """Represents a meshed volume: call mesher.mesh(labels), then mesher.get(label)."""
 
@@ -43,6 +79,9 @@ class Mesher:
     self._device = int(device)
     self._h = C.c_void_p()
     self._max_label = None
+    self._stage = None
+    self._blocks = []
+    self._erased = set()
     res = self._voxel_res
     rc = self._lib.zm_create(res.ctypes.data_as(C.POINTER(C.c_float)), self._device, C.byref(self._h))
     if rc != 0:
@@ -90,6 +129,8 @@ class Mesher:
     close: close meshes that touch the volume boundary (virtual one-voxel zero border).
     preserve_order: accepted for compatibility, ignored (as in the reference)."""
     res = _f3(self._voxel_res)
+    self._stage = None
+    self._erased = set()
     self._check(self._lib.zm_set_resolution(self._h, res.ctypes.data_as(C.POINTER(C.c_float))))
 
     cai = getattr(data, "__cuda_array_interface__", None)
@@ -222,7 +263,66 @@ class Mesher:
     voxel_centered: centre the mesh in the voxel (0.5, 0.5, 0.5) instead of at (0, 0, 0)."""
     if reduction_factor:
       raise NotImplementedError("zmesh_b200 covers reduction_factor=0 only (no mesh simplification)")
-    return self._fetch(label, bool(normals), bool(voxel_centered), transpose=False)
+    return self._get_staged(label, bool(normals), bool(voxel_centered))
+
+  # All labels are finalized on the device by the first get(); their arrays cross PCIe in ONE
+  # transfer into pinned host memory and get() hands out per-label views of it (SURVEY.md 8b:
+  # "get() becomes a slice of pinned host memory").  A label asked for twice gets a private copy the
+  # second time, so two results never alias.
+  def _pinned(self, nbytes: int) -> _PinnedBlock:
+    for b in self._blocks:
+      if b.nbytes >= nbytes and b.idle():
+        return b
+    self._blocks = [b for b in self._blocks if not b.idle()][-2:]
+    b = _PinnedBlock(self._lib, nbytes)
+    self._blocks.append(b)
+    return b
+
+  def _build_stage(self, normals: bool, voxel_centered: bool) -> "_Stage":
+    key = (voxel_centered, tuple(float(x) for x in self._voxel_res) if voxel_centered else None)
+    self._stage = None
+    off = _f3(self._voxel_res)
+    view = _lib.zm_bulk_view()
+    self._check(self._lib.zm_finalize(self._h, int(normals), int(voxel_centered), 0,
+                                      off.ctypes.data_as(C.POINTER(C.c_float)), C.byref(view)))
+    nv, nf, nl = int(view.n_vertices), int(view.n_faces), int(view.n_labels)
+    blk = self._pinned(12 * nv * (2 if normals else 1) + 12 * nf)
+    st = _Stage()
+    st.key = key
+    st.v = blk.view(np.float32, (nv, 3), 0)
+    st.f = blk.view(np.uint32, (nf, 3), 12 * nv)
+    st.n = blk.view(np.float32, (nv, 3), 12 * nv + 12 * nf) if normals else None
+    if nv or nf:
+      self._check(self._lib.zm_fetch_all(self._h, C.c_void_p(st.v.ctypes.data), C.c_void_p(st.f.ctypes.data),
+                                         C.c_void_p(st.n.ctypes.data) if normals else None))
+    labels = np.ctypeslib.as_array(view.labels_host, shape=(nl,)).tolist() if nl else []
+    voff = np.ctypeslib.as_array(view.voff_host, shape=(nl + 1,)).tolist() if nl else [0]
+    foff = np.ctypeslib.as_array(view.foff_host, shape=(nl + 1,)).tolist() if nl else [0]
+    st.index = {labels[i]: (voff[i], voff[i + 1], foff[i], foff[i + 1]) for i in range(nl)}
+    st.given = set()
+    self._stage = st
+    return st
+
+  def _get_staged(self, label, normals: bool, voxel_centered: bool) -> Mesh:
+    label = self._label_arg(label)
+    st = self._stage
+    key = (voxel_centered, tuple(float(x) for x in self._voxel_res) if voxel_centered else None)
+    if st is None or st.key != key or (normals and st.n is None):
+      st = self._build_stage(normals or (st is not None and st.key == key and st.n is not None), voxel_centered)
+    rng = st.index.get(label)
+    if rng is None or label in self._erased or rng[3] == rng[2]:
+      mesh = Mesh()
+      mesh.id = label
+      return mesh
+    v, f = st.v[rng[0]:rng[1]], st.f[rng[2]:rng[3]]
+    if label in st.given:
+      v, f = v.copy(), f.copy()
+    st.given.add(label)
+    mesh = Mesh(v, f, None)
+    if normals:
+      mesh.normals = st.n[rng[0]:rng[1]].astype(np.float64)  # the reference hands back float64 (zmesh/_zmesh.pyx:151)
+    mesh.id = label
+    return mesh
 
   def get_mesh(self, mesh_id, normals=False, simplification_factor=0, max_simplification_error=40,
                voxel_centered=False) -> Mesh:
@@ -246,10 +346,13 @@ class Mesher:
 
   def erase(self, segid) -> bool:
     existed = C.c_int(0)
-    self._check(self._lib.zm_erase(self._h, self._label_arg(segid), C.byref(existed)))
+    label = self._label_arg(segid)
+    self._check(self._lib.zm_erase(self._h, label, C.byref(existed)))
+    self._erased.add(label)
     return bool(existed.value)
 
   def clear(self):
+    self._stage = None
     self._check(self._lib.zm_clear(self._h))
 
   # -- extras (no reference counterpart) ------------------------------------------------------------
