@@ -185,7 +185,7 @@ def cpu_sample(name, wl):
   """Bounded sample of the workload for the CPU arm (about 5-15 s of single-core work)."""
   shape = wl["shape"]
   if wl["kind"] == "voronoi":
-    nz = max(8, min(shape[2], int(48e6 // (shape[0] * shape[1]))))
+    nz = max(8, min(shape[2], int(1.08e9 // (shape[0] * shape[1]))))  # ~1 Gvoxel: about 10 s on one core
     try:
       import torch
       if torch.cuda.is_available():
@@ -204,8 +204,8 @@ def cpu_sample(name, wl):
     v = host_volume(name, wl, (0, 24))
     return v, f"z-planes [0,24) of the workload volume ({shape[0]}x{shape[1]}x24)"
   if wl["kind"] == "connectomics":
-    v = host_volume(name, wl, (0, 160))
-    return v, "z-planes [0,160) of connectomics.npy (512x512x160)"
+    v = host_volume(name, wl)
+    return v, "the full volume (connectomics.npy 512x512x512)"
   v = host_volume(name, wl)
   return v, "full volume"
 

@@ -143,9 +143,10 @@ KernelSet kernel_set(int label_bytes, bool c_order) {
   }
 }
 
-pass2_fn faces_kernel(bool c_order, bool normals) {
-  if (c_order) return normals ? k_faces<true, true> : k_faces<true, false>;
-  return normals ? k_faces<false, true> : k_faces<false, false>;
+pass2_fn faces_kernel(bool c_order, bool normals, bool slab) {
+  if (slab) return c_order ? k_faces<true, false, true> : k_faces<false, false, true>;  // (no normals for slabs yet)
+  if (c_order) return normals ? k_faces<true, true, false> : k_faces<true, false, false>;
+  return normals ? k_faces<false, true, false> : k_faces<false, false, false>;
 }
 pass2_fn vertices_kernel(bool c_order) { return c_order ? k_vertices<true> : k_vertices<false>; }
 
@@ -504,7 +505,7 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     a.write_verts = same_verts ? 0 : 1;
     a.normalize = need_normals ? 1 : 0;
     if (need_faces || need_normals) {
-      faces_kernel(h->c_order, need_normals)<<<h->n_work, NT, 0, st>>>(h->vp, a);
+      faces_kernel(h->c_order, need_normals, h->slab_mode)<<<h->n_work, NT, 0, st>>>(h->vp, a);
       ZM_CUDA(h, cudaGetLastError());
       ++launches;
     }

@@ -47,6 +47,7 @@ constexpr int NT = 256;  // threads per CTA: warp w handles the s-plane w of the
 constexpr int NW = NT / 32;
 constexpr int RM = TM + 1, RS = TS + 1;  // staged label region (halo 1 on the high side)
 constexpr int TILE_VOX = TF * TM * TS;
+constexpr uint32_t PREFETCH_DISTANCE = 148 * 6;  // tiles ahead (in launch order) whose region is pulled into L2
 static_assert(TS == NW, "one warp per s-plane of the tile");
 
 // staged row length: a multiple of 16 bytes (TMA box constraint) that holds TF+1 voxels plus, for
@@ -179,6 +180,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
       ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -295,7 +300,7 @@ extern __shared__ __align__(128) unsigned char zm_dyn_smem[];
 // uniformity and the voxel's slot mask.  INTERIOR tiles (no volume boundary within reach) skip all
 // validity logic; a step whose 32 cubes are all uniform costs ~25 instructions.
 template <typename L, int MODE, bool INTERIOR>
-__device__ __forceinline__ void scan_tile(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const L* lab,
+__device__ __forceinline__ bool scan_tile(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const L* lab,
                                           uint32_t ef0, uint32_t em0, uint32_t es0) {
   constexpr int RFP = P1Smem<L, MODE>::RFP;
   constexpr uint32_t FULL = 0xffffffffu;
@@ -310,6 +315,7 @@ __device__ __forceinline__ void scan_tile(const VolParams& vp, const Pass1Args& 
   bool eq_row = !nef && !nes && a == p[RM * RFP + 1];  // the 4 corners of row j agree
   bool za = a != 0, zf = af != 0, zs = as_ != 0;
   uint8_t* orow = o.own6 + ((size_t)es * vp.Em + em0) * vp.Efp + ef;
+  bool any = false;
 #pragma unroll
   for (int j = 0; j < TM; ++j) {
     p += RFP;
@@ -336,6 +342,7 @@ __device__ __forceinline__ void scan_tile(const VolParams& vp, const Pass1Args& 
     const uint32_t ab = __ballot_sync(FULL, act);
     uint32_t rowtotal = 0;
     if (ab) {
+      any = true;
       if (INTERIOR) {
         if (nef) m |= (za ? 1u : 0u) | (zf ? 2u : 0u);
         if (nem) m |= (za ? 4u : 0u) | (zm ? 8u : 0u);
@@ -355,6 +362,7 @@ __device__ __forceinline__ void scan_tile(const VolParams& vp, const Pass1Args& 
     nef = nef2; nes = nes2; eq_row = eq_row2;
     za = zm; zf = amf != 0; zs = ams != 0;
   }
+  return any;
 }
 
 template <typename L, bool CO, int MODE>
@@ -383,6 +391,15 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
       fence_proxy_async();
       mbar_expect_tx(&S.mbar, (uint32_t)(sizeof(L) * RS * RM * RFP));
       tma_load_3d(S.lab, tmap, &S.mbar, (int)ef0 - (vp.pad ? ALIGN : 0), (int)em0 - (int)vp.pad, (int)es0 + vp.s_shift);
+      if (MODE == 0) {  // pull the tile a later CTA will stage into L2 now
+        uint32_t pt = tile + PREFETCH_DISTANCE;
+        if (pt < vp.ntf * vp.ntm * vp.nts) {
+          const uint32_t ptf = pt % vp.ntf;
+          pt /= vp.ntf;
+          tma_prefetch_3d(tmap, (int)(ptf * TF) - (vp.pad ? ALIGN : 0), (int)((pt % vp.ntm) * TM) - (int)vp.pad,
+                          (int)((pt / vp.ntm) * TS) + vp.s_shift);
+        }
+      }
     }
   } else {
     const L* __restrict__ src = static_cast<const L*>(vp.data);
@@ -396,20 +413,22 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
       lab[(ls * RM + lm) * RFP + lf] = v;
     }
   }
+  S.tricount[tid] = TRI_COUNT_D[tid];
   for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
   if (tid == 0) { S.nact = 0; S.nrec = 0; S.nlab = 0; S.overflow = 0; S.ci = 0; S.ttot = 0; }
+  __syncthreads();  // mbarrier initialised, tables cleared, (plain-load path) region staged
   if (vp.use_tma) {
-    mbar_wait(&S.mbar, parity);
+    mbar_wait(&S.mbar, parity);  // every thread waits itself: the TMA writes are visible to it afterwards
     parity ^= 1u;
   }
-  __syncthreads();
 
   // ---- S1: slot masks, in-row prefixes, compaction of active voxels ----
+  bool any;
   if (ef0 + TF + 1 <= vp.Ef && em0 + TM + 1 <= vp.Em && es0 + TS + 1 <= vp.Es)
-    scan_tile<L, MODE, true>(vp, o, S, lab, ef0, em0, es0);
+    any = scan_tile<L, MODE, true>(vp, o, S, lab, ef0, em0, es0);
   else
-    scan_tile<L, MODE, false>(vp, o, S, lab, ef0, em0, es0);
-  __syncthreads();
+    any = scan_tile<L, MODE, false>(vp, o, S, lab, ef0, em0, es0);
+  if (!__syncthreads_or(any ? 1 : 0)) return;  // uniform tile: nothing but the own6 zeros
 
   // ---- S2: row bases inside the tile ----
   if (warp == 0) {
@@ -427,7 +446,6 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
   }
   __syncthreads();
   const uint32_t nslots = S.nslots, nact = S.nact;
-  if (nslots == 0u && nact == 0u) return;  // uniform tile: nothing but the own6 zeros
   if (MODE == 0 && nslots > (uint32_t)VCAP) {
     if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
     return;
@@ -604,8 +622,6 @@ __global__ void __launch_bounds__(NT) k_classify(const VolParams vp, const __gri
     mbar_init(&S.mbar, 1);
     fence_mbar_init();
   }
-  S.tricount[threadIdx.x] = TRI_COUNT_D[threadIdx.x];
-  __syncthreads();
   uint32_t parity = 0;
   if (MODE == 0) {
     classify_tile<L, CO, MODE>(vp, &tmap, o, S, blockIdx.x, parity);
@@ -888,7 +904,7 @@ __device__ __forceinline__ TileHdr load_hdr(const TileHdr* p) {
 // into (triangle, corner) items so that every lane does exactly one vertex lookup and one 4-byte
 // store, consecutive lanes writing consecutive words of the face array.
 constexpr int FW = TF + 1;  // row pitch of the staged own6 region
-template <bool CO, bool NORMALS>
+template <bool CO, bool NORMALS, bool SLAB>
 __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams vp, const Pass2Args a) {
   constexpr uint32_t FULL = 0xffffffffu;
   constexpr int NROW = RM * RS;                   // 81 rows of TF+1 voxels
@@ -949,7 +965,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
         uint32_t pre = 0, rowtotal;
         if (__ballot_sync(FULL, m != 0u)) pre = warp_prefix3(__popc(m), ltm, rowtotal);
         const int ls = r / RM, lm = r - ls * RM;
-        if (es0 + ls == vp.Es_own && vp.Es_own < vp.Es) {
+        if (SLAB && es0 + ls == vp.Es_own && vp.Es_own < vp.Es) {
           // top plane of a slab: its slots belong to the next shard; look them up in a.foreign
           const uint32_t fbase = 0x80000000u | ((em0 + lm) * vp.Efp + ef0);
           o6[r * FW + lane] = 0;
@@ -991,7 +1007,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
       const uint32_t lf = vidx & 31u, lm = (vidx >> 5) & 7u, ls = vidx >> 8;
       ru[warp][lane] = ((ls * RM + lm) * FW + lf) | (cs << 16);
       rf[warp][lane] = e.b + old + pre;
-      rvo[warp][lane] = (uint32_t)(e.a >> 32);
+      if (SLAB) rvo[warp][lane] = (uint32_t)(e.a >> 32);
       if (NORMALS) rv[warp][lane] = e.a & 0xFFFFFFFFull;
       for (uint32_t t = 0; t < nt; ++t) tlist[warp][tpre + t] = (uint8_t)((lane << 3) | t);
     }
@@ -1010,8 +1026,8 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
       const uint32_t slot = (en >> 9) & 7u;
       const uint32_t gv = gb[u];
       uint32_t vi;
-      if (gv & 0x80000000u) vi = __ldg(a.foreign + 4ull * (gv & 0x7FFFFFFFu) + slot);
-      else vi = __ldg(a.perm + gv + __popc((uint32_t)o6[u] & ((1u << slot) - 1u))) + rvo[warp][src];
+      if (SLAB && (gv & 0x80000000u)) vi = __ldg(a.foreign + 4ull * (gv & 0x7FFFFFFFu) + slot);
+      else vi = __ldg(a.perm + gv + __popc((uint32_t)o6[u] & ((1u << slot) - 1u))) + (SLAB ? rvo[warp][src] : 0u);
       if (a.write_faces) a.faces[3ull * (rf[warp][src] + t) + k] = vi;
       if (NORMALS) {
         // the lane owning corner k recomputes the face normal from the cube geometry (no loads)
@@ -1023,7 +1039,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
           slot_position<CO>(vp, a, ef0 + lf + ((ec >> 12) & 1u), em0 + lm + ((ec >> 13) & 1u),
                             es0 + ls + ((ec >> 14) & 1u), ((ec >> 9) & 7u) >> 1, p[c][0], p[c][1], p[c][2]);
         }
-        float* dst = a.normals + 3ull * (rv[warp][src] + vi - rvo[warp][src]);
+        float* dst = a.normals + 3ull * (rv[warp][src] + vi - (SLAB ? rvo[warp][src] : 0u));
         // legacy faces (t0,t2,t1) = the stored row reversed: corner k becomes corner 2-k
         if (a.transpose) face_normal_corner(p[2], p[1], p[0], 2 - (int)k, dst);
         else face_normal_corner(p[0], p[1], p[2], (int)k, dst);
