@@ -158,7 +158,7 @@ __host__ __device__ constexpr uint32_t edge_info(int e) {
   int oc = 0;
   for (int n = 0; n < 8; ++n)
     if (corner_df<CO>(n) == of && corner_dm<CO>(n) == om && corner_ds<CO>(n) == os) oc = n;
-  int delta = (os * RM + om) * (TF + 1) + of;
+  int delta = (os * RM + om) * 48 + of;
   return (uint32_t)(delta | ((2 * axis) << 12) | (oc << 16) | (of << 20) | (om << 21) | (os << 22));
 }
 
@@ -179,6 +179,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
@@ -903,14 +910,14 @@ __device__ __forceinline__ TileHdr load_hdr(const TileHdr* p) {
 // faces: one CTA per non-empty tile.  Records are read 32 per warp; their triangles are expanded
 // into (triangle, corner) items so that every lane does exactly one vertex lookup and one 4-byte
 // store, consecutive lanes writing consecutive words of the face array.
-constexpr int FW = TF + 1;  // row pitch of the staged own6 region
+constexpr int FW = 48;  // row pitch of the staged own6 region: 32 voxels + the halo voxel, 16-byte aligned rows (cp.async)
 template <bool CO, bool NORMALS, bool SLAB>
 __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams vp, const Pass2Args a) {
   constexpr uint32_t FULL = 0xffffffffu;
   constexpr int NROW = RM * RS;                   // 81 rows of TF+1 voxels
-  constexpr int RPW = (NROW + NW - 1) / NW;       // rows per warp
   __shared__ uint32_t gb[NROW * FW];      // spatial id of the first slot of each region voxel
-  __shared__ uint8_t o6[NROW * FW];
+  __shared__ __align__(16) uint8_t o6[NROW * FW];
+  __shared__ uint32_t rbs[NROW][2];       // row bases: this tile column, next tile column
   __shared__ uint32_t cur[Caps<1>::LT / 2];  // running face cursors per tile-local label, two 16-bit halves per word
   __shared__ __align__(16) uint16_t s_tab[256 * 16];
   __shared__ uint8_t s_tricount[256];
@@ -940,47 +947,49 @@ __global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams v
     dst[tid + NT] = src[tid + NT];
   }
   for (uint32_t i = tid; i < (h.nlab + 1u) / 2u; i += NT) cur[i] = 0u;
-  const bool more = tf + 1 < vp.ntf;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    constexpr int HB = (RPW + 1) / 2;
-    uint32_t mrow[HB], rbrow[HB], mh[HB], rbh[HB];
-#pragma unroll
-    for (int i = 0; i < HB; ++i) {
-      const int r = warp + NW * (half * HB + i);
+  // stage the own6 bytes of the (TF+1)(TM+1)(TS+1) voxels whose slots the tile's cubes can reference
+  // and the row bases with cp.async (LDGSTS): 2 x 16 B + 4 B (halo voxel = first voxel of the next
+  // tile's row) + 2 x 4 B per row, no register staging
+  {
+    const bool more = tf + 1 < vp.ntf;
+    for (int i = tid; i < 5 * NROW; i += NT) {
+      const int r = i / 5, part = i - 5 * r;
       const int ls = r / RM, lm = r - ls * RM;
       const uint32_t em = em0 + lm, es = es0 + ls;
-      const bool rowvalid = r < NROW && em < vp.Em && es < vp.Es_own;
+      const bool rowvalid = em < vp.Em && es < vp.Es_own;
       const size_t row = (size_t)es * vp.Em + em;
-      mrow[i] = rowvalid ? a.own6[row * vp.Efp + ef0 + lane] : 0u;
-      rbrow[i] = rowvalid ? __ldg(a.rowbase + row * vp.ntf + tf) : 0u;
-      mh[i] = (rowvalid && more) ? a.own6[row * vp.Efp + ef0 + TF] : 0u;  // halo column: next tile's first voxel
-      rbh[i] = (rowvalid && more) ? __ldg(a.rowbase + row * vp.ntf + tf + 1) : 0u;
-    }
-#pragma unroll
-    for (int i = 0; i < HB; ++i) {
-      const int r = warp + NW * (half * HB + i);
-      if (r < NROW) {
-        const uint32_t m = mrow[i];
-        uint32_t pre = 0, rowtotal;
-        if (__ballot_sync(FULL, m != 0u)) pre = warp_prefix3(__popc(m), ltm, rowtotal);
-        const int ls = r / RM, lm = r - ls * RM;
-        if (SLAB && es0 + ls == vp.Es_own && vp.Es_own < vp.Es) {
-          // top plane of a slab: its slots belong to the next shard; look them up in a.foreign
-          const uint32_t fbase = 0x80000000u | ((em0 + lm) * vp.Efp + ef0);
-          o6[r * FW + lane] = 0;
-          gb[r * FW + lane] = fbase + lane;
-          if (lane == 0) { o6[r * FW + TF] = 0; gb[r * FW + TF] = fbase + TF; }
-        } else {
-          o6[r * FW + lane] = (uint8_t)m;
-          gb[r * FW + lane] = rbrow[i] + pre;
-          if (lane == 0) {
-            o6[r * FW + TF] = (uint8_t)mh[i];
-            gb[r * FW + TF] = rbh[i];
-          }
-        }
+      if (part < 2) {
+        if (rowvalid) cp_async<16>(&o6[r * FW + 16 * part], a.own6 + row * vp.Efp + ef0 + 16 * part);
+        else *reinterpret_cast<uint4*>(&o6[r * FW + 16 * part]) = make_uint4(0u, 0u, 0u, 0u);
+      } else if (part == 2) {
+        if (rowvalid && more) cp_async<4>(&o6[r * FW + TF], a.own6 + row * vp.Efp + ef0 + TF);
+        else *reinterpret_cast<uint32_t*>(&o6[r * FW + TF]) = 0u;
+      } else {
+        const int c = part - 3;
+        if (rowvalid && (c == 0 || more)) cp_async<4>(&rbs[r][c], a.rowbase + row * vp.ntf + tf + c);
+        else rbs[r][c] = 0u;
       }
     }
+    cp_async_wait_all();
+  }
+  __syncthreads();
+  // spatial id of each region voxel's first slot (only rows that have slots need it)
+  for (int r = warp; r < NROW; r += NW) {
+    const int ls = r / RM, lm = r - ls * RM;
+    if (SLAB && es0 + ls == vp.Es_own && vp.Es_own < vp.Es) {
+      // top plane of a slab: its slots belong to the next shard; look them up in a.foreign
+      const uint32_t fbase = 0x80000000u | ((em0 + lm) * vp.Efp + ef0);
+      gb[r * FW + lane] = fbase + lane;
+      if (lane == 0) gb[r * FW + TF] = fbase + TF;
+      continue;
+    }
+    const uint32_t m = o6[r * FW + lane];
+    if (__ballot_sync(FULL, m != 0u)) {
+      uint32_t rowtotal;
+      const uint32_t pre = warp_prefix3(__popc(m), ltm, rowtotal);
+      gb[r * FW + lane] = rbs[r][0] + pre;
+    }
+    if (lane == 0) gb[r * FW + TF] = rbs[r][1];
   }
   __syncthreads();
 
