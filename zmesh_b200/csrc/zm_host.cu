@@ -55,6 +55,7 @@ struct FinalState {
 
 struct zm_handle {
   int device = 0;
+  int num_sms = 148;
   cudaStream_t stream = nullptr;      // the stream all work is queued on
   cudaStream_t own_stream = nullptr;  // created by zm_create (stream == own_stream unless zm_set_stream)
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -67,7 +68,7 @@ struct zm_handle {
 
   // scratch + intermediates (device)
   DevBuf d_vol, d_keys, d_cnt, d_offV, d_offT, d_list, d_partial, d_ctl;
-  DevBuf d_own6, d_rowbase, d_perm, d_vinfo, d_rec, d_tl, d_hdr, d_dense;
+  DevBuf d_rowinfo, d_perm, d_vinfo, d_rec, d_tl, d_hdr, d_dense;
   // results (device)
   DevBuf d_faces, d_verts, d_normals;
   DevBuf d_voff, d_tmpA, d_tmpB;     // slab sharding: per-table-slot index offsets; upload scratch
@@ -115,12 +116,13 @@ int fail(zm_handle* h, int code, const std::string& msg) {
 }
 
 typedef void (*classify_fn)(const VolParams, const CUtensorMap, const Pass1Args);
-typedef void (*pass2_fn)(const VolParams, const Pass2Args);
+typedef void (*pass2_fn)(const VolParams, const CUtensorMap, const Pass2Args);
 
 struct KernelSet {
   classify_fn classify[2];  // MODE 0 / MODE 1
   size_t smem[2];
   int row_pad;              // staged row length (elements) = TMA box extent along f
+  int grid0 = 0;            // persistent grid of the MODE 0 launch (filled by run_mesh)
 };
 
 template <typename L, bool CO>
@@ -143,12 +145,11 @@ KernelSet kernel_set(int label_bytes, bool c_order) {
   }
 }
 
-pass2_fn faces_kernel(bool c_order, bool normals, bool slab) {
-  if (slab) return c_order ? k_faces<true, false, true> : k_faces<false, false, true>;  // (no normals for slabs yet)
-  if (c_order) return normals ? k_faces<true, true, false> : k_faces<true, false, false>;
-  return normals ? k_faces<false, true, false> : k_faces<false, false, false>;
+pass2_fn emit_kernel(bool c_order, bool normals, bool slab) {
+  if (slab) return c_order ? k_emit<true, false, true> : k_emit<false, false, true>;  // (no normals for slabs yet)
+  if (c_order) return normals ? k_emit<true, true, false> : k_emit<true, false, false>;
+  return normals ? k_emit<false, true, false> : k_emit<false, false, false>;
 }
-pass2_fn vertices_kernel(bool c_order) { return c_order ? k_vertices<true> : k_vertices<false>; }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -192,16 +193,33 @@ bool make_tensor_map(CUtensorMap* tm, const void* data, int label_bytes, uint32_
   return r == CUDA_SUCCESS;
 }
 
+// TMA descriptor of rowinfo viewed as uint32 [Es][Em][ntf * RI_WORDS]; box = the (TM+1)(TS+1) rows x
+// two row segments a tile's cubes can reference (k_emit).  Out-of-range rows / segments read as zero
+// (= no slots).
+bool make_rowinfo_map(CUtensorMap* tm, const void* rowinfo, const VolParams& vp) {
+  memset(tm, 0, sizeof(*tm));
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)vp.ntf * RI_WORDS, vp.Em, vp.Es};
+  cuuint64_t strides[2] = {(cuuint64_t)vp.ntf * RI_WORDS * 4, (cuuint64_t)vp.ntf * RI_WORDS * 4 * vp.Em};
+  cuuint32_t box[3] = {(cuuint32_t)RGN_WORDS, (cuuint32_t)RM, (cuuint32_t)RS};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(rowinfo), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int prepare_device(zm_handle* h) {
   // case tables -> device globals; opt in to > 48 KB of shared memory per CTA
   ZM_CUDA(h, cudaMemcpyToSymbol(TRI_COUNT_D, TRI_COUNT, sizeof(TRI_COUNT)));
   static_assert(sizeof(TRI_NIBBLES) == 256 * sizeof(unsigned long long), "table size");
   ZM_CUDA(h, cudaMemcpyToSymbol(TRI_NIBBLES_D, TRI_NIBBLES, sizeof(TRI_NIBBLES)));
   {
-    std::vector<uint16_t> tab(2 * 256 * 16);
+    std::vector<uint32_t> tab(2 * 256 * CASE_TRIS);
     build_case_table<false>(tab.data());
-    build_case_table<true>(tab.data() + 256 * 16);
-    ZM_CUDA(h, cudaMemcpyToSymbol(CASE_TAB_D, tab.data(), tab.size() * sizeof(uint16_t)));
+    build_case_table<true>(tab.data() + 256 * CASE_TRIS);
+    ZM_CUDA(h, cudaMemcpyToSymbol(CASE_TAB_D, tab.data(), tab.size() * sizeof(uint32_t)));
   }
   for (int lb : {1, 2, 4, 8})
     for (int co = 0; co < 2; ++co) {
@@ -298,14 +316,18 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   }
   ZM_CUDA(h, cudaEventRecord(h->ev[1], st));
 
-  const KernelSet ks = kernel_set(label_bytes, c_order != 0);
+  KernelSet ks = kernel_set(label_bytes, c_order != 0);
+  {
+    int per_sm = 0;
+    ZM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)ks.classify[0], NT, ks.smem[0]));
+    ks.grid0 = h->num_sms * std::max(per_sm, 1);
+  }
   CUtensorMap tmap;
   vp.use_tma = make_tensor_map(&tmap, vp.data, label_bytes, vp.nf, vp.nm, vp.ns, ks.row_pad) ? 1u : 0u;
 
   const size_t nrows = (size_t)vp.Es * vp.Em * vp.ntf;
-  ZM_CUDA(h, h->d_own6.ensure((size_t)vp.Es * vp.Em * vp.Efp));
-  ZM_CUDA(h, h->d_rowbase.ensure(nrows * sizeof(uint32_t)));
-  ZM_CUDA(h, h->d_hdr.ensure((size_t)ntiles * sizeof(TileHdr)));
+  ZM_CUDA(h, h->d_rowinfo.ensure(nrows * RI_WORDS * sizeof(uint32_t)));
+  ZM_CUDA(h, h->d_hdr.ensure((size_t)ntiles * 2 * sizeof(TileHdr)));  // a dense tile is emitted as two half tiles
   ZM_CUDA(h, h->d_dense.ensure((size_t)ntiles * 4));
   ZM_CUDA(h, h->d_ctl.ensure(sizeof(Control)));
   ZM_CUDA(h, h->d_partial.ensure(3 * 1024 * 8));
@@ -328,17 +350,17 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
     ZM_CUDA(h, h->d_list.ensure((size_t)cap * 24));
     ZM_CUDA(h, h->d_perm.ensure((size_t)capV * 4));
     ZM_CUDA(h, h->d_vinfo.ensure((size_t)capV * 4));
-    ZM_CUDA(h, h->d_rec.ensure((size_t)capR * 4));
+    ZM_CUDA(h, h->d_rec.ensure((size_t)capR * 8));
     ZM_CUDA(h, h->d_tl.ensure((size_t)capL * sizeof(TLEntry)));
     ZM_CUDA(h, cudaMemsetAsync(h->d_keys.p, 0, (size_t)cap * 8, st));
     ZM_CUDA(h, cudaMemsetAsync(h->d_cnt.p, 0, (size_t)cap * 8, st));
     ZM_CUDA(h, cudaMemsetAsync(h->d_ctl.p, 0, sizeof(Control), st));
 
     LabelTable ht{h->d_keys.as<u64>(), h->d_cnt.as<u64>(), cap - 1};
-    Pass1Args p1{ht, d_ctl, h->d_own6.as<uint8_t>(), h->d_rowbase.as<uint32_t>(), h->d_perm.as<uint32_t>(),
-                 h->d_vinfo.as<uint32_t>(), h->d_rec.as<uint32_t>(), h->d_tl.as<TLEntry>(), h->d_hdr.as<TileHdr>(),
+    Pass1Args p1{ht, d_ctl, h->d_rowinfo.as<uint32_t>(), h->d_perm.as<uint32_t>(),
+                 h->d_vinfo.as<uint32_t>(), h->d_rec.as<u64>(), h->d_tl.as<TLEntry>(), h->d_hdr.as<TileHdr>(),
                  h->d_dense.as<uint32_t>(), capV, capR, capL};
-    ks.classify[0]<<<(uint32_t)ntiles, NT, ks.smem[0], st>>>(vp, tmap, p1);
+    ks.classify[0]<<<(uint32_t)std::min<unsigned long long>(ntiles, (unsigned long long)ks.grid0), NT, ks.smem[0], st>>>(vp, tmap, p1);
     ZM_CUDA(h, cudaGetLastError());
     const uint32_t dense_grid = (uint32_t)std::min<unsigned long long>(ntiles, 148ull);
     ks.classify[1]<<<dense_grid, NT, ks.smem[1], st>>>(vp, tmap, p1);
@@ -452,11 +474,10 @@ int ensure_tl_fixed(zm_handle* h) {
 Pass2Args pass2_args(zm_handle* h) {
   Pass2Args a{};
   a.hdr = h->d_hdr.as<TileHdr>();
-  a.own6 = h->d_own6.as<uint8_t>();
-  a.rowbase = h->d_rowbase.as<uint32_t>();
   a.perm = h->d_perm.as<uint32_t>();
   a.vinfo = h->d_vinfo.as<uint32_t>();
-  a.rec = h->d_rec.as<uint32_t>();
+  a.rec = h->d_rec.as<u64>();
+  a.n_work = h->n_work;
   a.tl = h->d_tl.as<TLEntry>();
   a.foreign = h->foreign;
   return a;
@@ -503,15 +524,20 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     a.transpose = transpose;
     a.write_faces = need_faces ? 1 : 0;
     a.write_verts = same_verts ? 0 : 1;
-    a.normalize = need_normals ? 1 : 0;
-    if (need_faces || need_normals) {
-      faces_kernel(h->c_order, need_normals, h->slab_mode)<<<h->n_work, NT, 0, st>>>(h->vp, a);
+    {
+      CUtensorMap rmap;
+      if (!make_rowinfo_map(&rmap, h->d_rowinfo.p, h->vp)) return fail(h, ZM_ERR_CUDA, "cuTensorMapEncodeTiled(rowinfo) failed");
+      pass2_fn fn = emit_kernel(h->c_order, need_normals, h->slab_mode);
+      int per_sm = 0;
+      ZM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, NT, 0));
+      const uint32_t grid = std::min<uint32_t>(h->n_work, (uint32_t)(h->num_sms * std::max(per_sm, 1)));
+      fn<<<grid, NT, 0, st>>>(h->vp, rmap, a);
       ZM_CUDA(h, cudaGetLastError());
       ++launches;
     }
     ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
-    if (!same_verts || need_normals) {
-      vertices_kernel(h->c_order)<<<h->n_work, NT_V, 0, st>>>(h->vp, a);
+    if (need_normals) {
+      k_normals_normalize<<<grid_for(h->Vtot, 256), 256, 0, st>>>(h->d_normals.as<float>(), h->Vtot);
       ZM_CUDA(h, cudaGetLastError());
       ++launches;
     }
@@ -565,6 +591,7 @@ int zm_create(const float resolution[3], int device, zm_handle** out) {
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || h->num_sms <= 0) h->num_sms = 148;
   h->stream = h->own_stream;
   for (auto& ev : h->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -584,7 +611,7 @@ void zm_destroy(zm_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_vol, &h->d_keys, &h->d_cnt, &h->d_offV, &h->d_offT, &h->d_list, &h->d_partial, &h->d_ctl,
-                    &h->d_own6, &h->d_rowbase, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_hdr,
+                    &h->d_rowinfo, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_hdr,
                     &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals, &h->d_voff, &h->d_tmpA, &h->d_tmpB})
     b->release();
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -765,8 +792,8 @@ int zm_clear(zm_handle* h) {
   drop_results(h);
   h->has_result = had;  // a cleared mesher answers like an empty one (marching_cubes.hpp:184-189)
   cudaSetDevice(h->device);
-  for (DevBuf* b : {&h->d_faces, &h->d_verts, &h->d_normals, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_own6,
-                    &h->d_rowbase, &h->d_vol})
+  for (DevBuf* b : {&h->d_faces, &h->d_verts, &h->d_normals, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_rowinfo,
+                    &h->d_vol})
     b->release();
   return ZM_OK;
 }

@@ -7,24 +7,32 @@
 //   * a vertex of label L is a voxel-grid edge (two axis-adjacent voxels) with exactly one
 //     endpoint == L.  Each grid edge is OWNED by its lower voxel, so every vertex is produced
 //     exactly once -- no hashing of vertices, no sort, no unique pass.
-//   * voxel u owns up to 6 vertex slots ("own6" mask): slot 2d+0 = (edge u -> u+d, label of u),
+//   * voxel u owns up to 6 vertex slots: slot 2d+0 = (edge u -> u+d, label of u),
 //     slot 2d+1 = (same edge, label of u+d), d = memory axis 0 (fastest) .. 2 (slowest).
-//   * vertices get a spatial id  g = rowbase[row(u)] + (#slots of earlier voxels in the row)
-//     + (#lower slots of u);  perm[g] = index of the vertex inside its label's vertex list.
+//   * a ROW SEGMENT (32 voxels of one tile along the fastest axis) stores its slots as six 32-bit
+//     bit planes (plane s, bit i = voxel i owns slot s) plus the spatial id of its first slot:
+//     `rowinfo` = 8 words per segment (= 1 byte per voxel).  Slots are numbered plane-major inside
+//     the segment:  g = rowbase + sum_{p<s} popc(plane_p) + popc(plane_s & ((1 << i) - 1)),
+//     so a lookup is two shared loads and a popc;  perm[g] = index of the vertex inside its
+//     label's vertex list.
 //
-// Pass 1 (k_classify, the only kernel that reads the label volume): one CTA per tile of
-// 32 x 8 x 8 voxels (+1 halo) staged in shared memory by TMA (cp.async.bulk.tensor.3d, zero fill
-// outside the volume = the `close` border for free).  Active voxels are compacted, distinct labels
-// of each cube enumerated, per-(tile,label) counts kept in a shared-memory table with
-// warp-aggregated atomics, one global reservation per (tile,label).  Outputs, all label-free:
-//   own6[voxel] (1 B), rowbase[row], perm[g] (4 B/vertex), vl[g] (2 B/vertex: tile-local label
-//   index), rec[] (4 B per (label,cube) pair: cube-in-tile | case | tile-local label index),
-//   tl[] (per (tile,label): label slot + face base), hdr[] work list of the non-empty tiles.
+// Pass 1 (k_classify, the only kernel that reads the label volume): persistent CTAs walk the tiles
+// of 32 x 8 x 8 voxels; the (+1 halo) label region is staged in shared memory by TMA
+// (cp.async.bulk.tensor.3d, zero fill outside the volume = the `close` border for free) and the
+// load of the CTA's next tile is issued as soon as the current region is dead.  A tile whose
+// whole region is one value is recognised with 16-byte compares and costs nothing else.  Active
+// voxels are compacted, distinct labels of each cube enumerated, per-(tile,label) counts kept in a
+// shared-memory table with warp-aggregated atomics, one global reservation per (tile,label).
+// Outputs, all label-free:
+//   rowinfo[row segment], perm[g] (4 B/vertex), vinfo[g] (4 B/vertex: voxel-in-tile, slot,
+//   tile-local label index), rec[] (8 B per (label,cube) pair: voxel-in-tile | case | tile-local
+//   label index, first face row inside the (tile,label) block), tl[] (per (tile,label): label slot
+//   + face base), hdr[] work list of the non-empty tiles.
 // Scan (k_scan_*) turns per-label counts into per-label output offsets; k_tl_fixup folds them into
-// tl[].  Pass 2 never touches labels again:
-//   k_faces    : one thread per record -> faces (uint32 triples) [+ face normals accumulation]
-//   k_vertices : one thread per owning voxel -> float32 vertices in the final form
-//                fl32(fl32(fl32(res*k) [+ off]) / 2) [+ normals normalisation]
+// tl[].  Pass 2 (k_emit) never touches labels again: persistent CTAs walk the work list, stage the
+// rowinfo region of a tile with one TMA load, and write faces (uint32 triples, one triangle per
+// lane) [+ face normals accumulation] and float32 vertices in the final form
+// fl32(fl32(fl32(res*k) [+ off]) / 2).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -47,11 +55,12 @@ constexpr int NT = 256;  // threads per CTA: warp w handles the s-plane w of the
 constexpr int NW = NT / 32;
 constexpr int RM = TM + 1, RS = TS + 1;  // staged label region (halo 1 on the high side)
 constexpr int TILE_VOX = TF * TM * TS;
-constexpr uint32_t PREFETCH_DISTANCE = 148 * 6;  // tiles ahead (in launch order) whose region is pulled into L2
+constexpr int NROWS = TM * TS;           // row segments per tile
+constexpr int RI_WORDS = 8;              // rowinfo words per row segment: planes 0..5, rowbase, spare
 static_assert(TS == NW, "one warp per s-plane of the tile");
 
 // staged row length: a multiple of 16 bytes (TMA box constraint) that holds TF+1 voxels plus, for
-// `close`, the 16/sizeof(L)-1 extra leading columns an aligned box start costs (see classify_tile)
+// `close`, the 16/sizeof(L)-1 extra leading columns an aligned box start costs (see stage coords)
 template <typename L> struct RowPad { static constexpr int value = ((TF + 1) * (int)sizeof(L) + 15) / 16 * 16 / (int)sizeof(L); };
 
 enum : uint32_t {
@@ -61,17 +70,17 @@ enum : uint32_t {
 };
 
 // capacities of the per-tile shared-memory structures.  MODE 0 covers ordinary segmentations;
-// tiles that overflow it are queued and redone by the MODE 1 launch, whose capacities are the
-// hard maxima of a tile (so it cannot overflow).
+// tiles that overflow it are queued and redone by the MODE 1 launch, which processes a tile as two
+// half tiles (4 s-planes each) whose capacities are the hard maxima (so it cannot overflow).
 template <int MODE> struct Caps;
-template <> struct Caps<0> { static constexpr int LT = 256, VCAP = 2048, RCAP = 2048, PROBES = 16; };
-template <> struct Caps<1> { static constexpr int LT = 4096, VCAP = 6 * TILE_VOX, RCAP = 8 * TILE_VOX, PROBES = 4096; };
+template <> struct Caps<0> { static constexpr int LT = 256, VCAP = 2048, RCAP = 2048, PROBES = 16, HALVES = 1; };
+template <> struct Caps<1> { static constexpr int LT = 2048, VCAP = 6 * TILE_VOX / 2, RCAP = 8 * TILE_VOX / 2, PROBES = 2048, HALVES = 2; };
 
 struct VolParams {
   const void* data;        // device pointer, memory order (f fastest, m, s slowest)
   uint32_t nf, nm, ns;     // input extents
   uint32_t Ef, Em, Es;     // extended extents = n + 2*pad (close => virtual zero border)
-  uint32_t Efp;            // ntf * TF: row pitch of own6[]
+  uint32_t Efp;            // ntf * TF: row pitch of the boundary-plane exchange buffers
   uint32_t pad;            // 1 when close
   uint32_t ntf, ntm, nts;  // tiles per axis
   uint32_t ox, oy, oz;     // shard origin in logical voxels (added to keys)
@@ -89,7 +98,7 @@ struct LabelTable {  // global open-addressing table, key 0 = empty (label 0 is 
   uint32_t mask;  // capacity - 1
 };
 
-struct __align__(16) TileHdr {  // one per non-empty tile, in work-list order
+struct __align__(16) TileHdr {  // one per non-empty (half) tile, in work-list order
   u64 recbase;
   uint32_t gbase;
   uint32_t tlbase;
@@ -112,13 +121,12 @@ struct Control {
 struct Pass1Args {
   LabelTable ht;
   Control* ctl;
-  uint8_t* own6;      // [Es][Em][Efp]
-  uint32_t* rowbase;  // [Es*Em*ntf]
+  uint32_t* rowinfo;  // [Es][Em][ntf][RI_WORDS]
   uint32_t* perm;     // [capV]
   uint32_t* vinfo;    // [capV]: voxel-in-tile | slot << 11 | tile-local label index << 14
-  uint32_t* rec;      // [capR]
+  u64* rec;           // [capR]: voxel-in-tile | case << 11 | tile-local label index << 19 | first face row in (tile,label) << 32
   TLEntry* tl;        // [capL]
-  TileHdr* hdr;       // [ntiles] work list of non-empty tiles
+  TileHdr* hdr;       // [ntiles * HALVES] work list of non-empty tiles
   uint32_t* dense_list;  // [ntiles]
   u64 capV, capR, capL;
 };
@@ -142,11 +150,9 @@ template <bool CO> __host__ __device__ constexpr int corner_plus_f() { return CO
 template <bool CO> __host__ __device__ constexpr int corner_plus_m() { return 4; }
 template <bool CO> __host__ __device__ constexpr int corner_plus_s() { return CO ? 1 : 3; }
 
-// pass-2 staged own6 region: (TF+1) x (TM+1) x (TS+1) voxels, row pitch TF+1
-
-// per edge: bits 0-9 region index delta of the owner voxel, bits 12-14 2*axis, bits 16-18 owner
-// corner, bits 20-22 owner offset (f,m,s).  The midpoint M = corner_a + corner_b (half-voxel
-// units): the axis is where M == 1, the owner (lower endpoint) is M >> 1.
+// per edge: bits 0-3 row delta (ds * RM + dm) of the owner voxel, bit 4 its f offset, bits 12-14
+// 2*axis, bits 16-18 owner corner.  The midpoint M = corner_a + corner_b (half-voxel units): the
+// axis is where M == 1, the owner (lower endpoint) is M >> 1.
 template <bool CO>
 __host__ __device__ constexpr uint32_t edge_info(int e) {
   int a = edge_a(e), b = edge_b(e);
@@ -158,8 +164,8 @@ __host__ __device__ constexpr uint32_t edge_info(int e) {
   int oc = 0;
   for (int n = 0; n < 8; ++n)
     if (corner_df<CO>(n) == of && corner_dm<CO>(n) == om && corner_ds<CO>(n) == os) oc = n;
-  int delta = (os * RM + om) * 48 + of;
-  return (uint32_t)(delta | ((2 * axis) << 12) | (oc << 16) | (of << 20) | (om << 21) | (os << 22));
+  int drow = os * RM + om;
+  return (uint32_t)(drow | (of << 4) | ((2 * axis) << 12) | (oc << 16));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -179,17 +185,6 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
-}
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
 }
 __device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
   uint32_t done;
@@ -277,37 +272,118 @@ __device__ __forceinline__ uint32_t group_prefix3(uint32_t c, uint32_t grp, uint
 template <typename L, int MODE>
 struct __align__(128) P1Smem {
   static constexpr int RFP = RowPad<L>::value;
-  union {
-    struct {
-      L lab[RS * RM * RFP];       // TMA destination: must stay first (128-byte aligned)
-      uint32_t alist[TILE_VOX];   // active voxels: voxel-in-tile | own6 << 11 | in-row slot prefix << 17
-    };
-    struct {                      // live from S5 on, when lab/alist are dead
-      uint32_t lvb[Caps<MODE>::LT];   // first rank of the tile's vertices inside the label
-      uint16_t cidx[Caps<MODE>::LT];  // tile-local (compact) label index
-    };
-  };
+  L lab[RS * RM * RFP];            // TMA destination: must stay first (128-byte aligned)
+  uint32_t pl[NROWS][RI_WORDS];    // per row segment: slot bit planes 0..5; [6] = slots of the row, then (S2) first slot of the row in the tile
+  uint32_t alist[TILE_VOX];        // active voxels: voxel-in-tile | slot mask << 11
   u64 lkeys[Caps<MODE>::LT];
   u64 mbar;
   u64 recbase;
-  uint32_t lcnt[Caps<MODE>::LT];  // low 16: vertices of the label in this tile, high 16: triangles
+  uint32_t lcnt[Caps<MODE>::LT];   // low 16: vertices of the label in this tile, high 16: triangles
+  uint32_t lvb[Caps<MODE>::LT];    // first rank of the tile's vertices inside the label
   uint32_t vstage[Caps<MODE>::VCAP];  // per tile-local slot: local rank << 12 | table slot
   uint32_t rstage[Caps<MODE>::RCAP];  // voxel-in-tile | case << 11 | table slot << 19
-  uint32_t rowcnt[TM * TS], rowpre[TM * TS];
+  uint32_t tc[2][4];               // tile coordinates (tf, tm, ts) published by the thread that issues the TMA load
   uint32_t nact, nrec, nlab, nslots, overflow, ok, gbase, tlbase, ci, ttot;
+  uint16_t pp[NROWS][8];           // tile-local index of the first slot of (row, plane)
+  uint16_t cidx[Caps<MODE>::LT];   // tile-local (compact) label index
   uint16_t pstage[Caps<MODE>::VCAP];  // per tile-local slot: voxel-in-tile | slot << 11
+  uint16_t rtoff[Caps<MODE>::RCAP];   // per record: first face row inside the (tile,label) block
   uint8_t tricount[256];
 };
 static_assert(sizeof(P1Smem<u64, 1>) <= 227 * 1024 && sizeof(P1Smem<uint8_t, 1>) <= 227 * 1024, "dense mode must fit one SM");
 
 extern __shared__ __align__(128) unsigned char zm_dyn_smem[];
 
-// S1 of classify_tile.  Thread (lane = f, warp = s) marches over m keeping the four labels of the
+// first staged column / row / plane of a tile in input coordinates.  TMA needs a 16-byte aligned
+// start along f: with the `close` border the box starts ALIGN elements (not 1) before the tile and
+// the region sits ALIGN-1 columns into the staged rows.
+template <typename L>
+__device__ __forceinline__ void stage_origin(const VolParams& vp, uint32_t tf, uint32_t tm, uint32_t ts, int& c0, int& c1, int& c2) {
+  constexpr int ALIGN = 16 / (int)sizeof(L);
+  c0 = (int)(tf * TF) - (vp.pad ? ALIGN : 0);
+  c1 = (int)(tm * TM) - (int)vp.pad;
+  c2 = (int)(ts * TS) + vp.s_shift;
+}
+
+// thread 0: publish the coordinates of `tile` in tc[slot] and (TMA path) start the load of its region
+template <typename L, int MODE>
+__device__ __forceinline__ void publish_tile(const VolParams& vp, P1Smem<L, MODE>& S, uint32_t tile, int slot) {
+  uint32_t b = tile;
+  const uint32_t tf = b % vp.ntf;
+  b /= vp.ntf;
+  S.tc[slot][0] = tf;
+  S.tc[slot][1] = b % vp.ntm;
+  S.tc[slot][2] = b / vp.ntm;
+}
+template <typename L, int MODE>
+__device__ __forceinline__ void issue_tile(const VolParams& vp, const CUtensorMap* tmap, P1Smem<L, MODE>& S, int slot) {
+  int c0, c1, c2;
+  stage_origin<L>(vp, S.tc[slot][0], S.tc[slot][1], S.tc[slot][2], c0, c1, c2);
+  fence_proxy_async();
+  mbar_expect_tx(&S.mbar, (uint32_t)(sizeof(L) * RS * RM * P1Smem<L, MODE>::RFP));
+  tma_load_3d(S.lab, tmap, &S.mbar, c0, c1, c2);
+}
+
+// volumes TMA cannot address (row pitch or base not 16-byte aligned): the same box with plain loads
+template <typename L, int MODE>
+__device__ __forceinline__ void stage_plain(const VolParams& vp, P1Smem<L, MODE>& S, uint32_t tf, uint32_t tm, uint32_t ts) {
+  constexpr int RFP = P1Smem<L, MODE>::RFP;
+  const L* __restrict__ src = static_cast<const L*>(vp.data);
+  int c0, c1, c2;
+  stage_origin<L>(vp, tf, tm, ts, c0, c1, c2);
+  for (int i = threadIdx.x; i < RFP * RM * RS; i += NT) {
+    const int lf = i % RFP;
+    const int t = i / RFP;
+    const int lm = t % RM, ls = t / RM;
+    const uint32_t jf = (uint32_t)(c0 + lf), jm = (uint32_t)(c1 + lm), js = (uint32_t)(c2 + ls);  // wraps when < 0
+    L v = 0;
+    if (jf < vp.nf && jm < vp.nm && js < vp.ns) v = src[((size_t)js * vp.nm + jm) * vp.nf + jf];
+    S.lab[i] = v;
+  }
+}
+
+// true iff every staged element equals the first one (then no cube of the tile is active and no
+// voxel owns a slot); 16-byte compares, one barrier
+template <typename L, int MODE>
+__device__ __forceinline__ bool region_uniform(const P1Smem<L, MODE>& S) {
+  constexpr int NQ = (int)sizeof(L) * RS * RM * P1Smem<L, MODE>::RFP / 16;
+  const uint4* q = reinterpret_cast<const uint4*>(S.lab);
+  uint4 ref;
+  if (sizeof(L) == 8) {
+    const uint2 r = *reinterpret_cast<const uint2*>(S.lab);
+    ref = make_uint4(r.x, r.y, r.x, r.y);
+  } else {
+    uint32_t r = *reinterpret_cast<const uint32_t*>(S.lab);
+    if (sizeof(L) == 2) r = __byte_perm(r, r, 0x1010);
+    if (sizeof(L) == 1) r = __byte_perm(r, r, 0x0000);
+    ref = make_uint4(r, r, r, r);
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = threadIdx.x; i < NQ; i += NT) {
+    const uint4 v = q[i];
+    acc |= (v.x ^ ref.x) | (v.y ^ ref.y) | (v.z ^ ref.z) | (v.w ^ ref.w);
+  }
+  return __syncthreads_and(acc == 0u) != 0;
+}
+
+// all-zero rowinfo for the row segments of a tile without slots
+__device__ __forceinline__ void zero_rows(const VolParams& vp, const Pass1Args& o, uint32_t tf, uint32_t tm, uint32_t ts) {
+  const int tid = threadIdx.x;
+  if (tid < 2 * NROWS) {
+    const int row = tid >> 1;
+    const uint32_t rs = ts * TS + row / TM, rm = tm * TM + row % TM;
+    if (rs < vp.Es_own && rm < vp.Em)
+      reinterpret_cast<uint4*>(o.rowinfo + (((size_t)rs * vp.Em + rm) * vp.ntf + tf) * RI_WORDS)[tid & 1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+// S1 of a tile.  Thread (lane = f, warp = s) marches over m keeping the four labels of the
 // previous row in registers: per step 4 shared loads and 4 label compares give the cube's
-// uniformity and the voxel's slot mask.  INTERIOR tiles (no volume boundary within reach) skip all
-// validity logic; a step whose 32 cubes are all uniform costs ~25 instructions.
+// uniformity and the voxel's slot mask; six ballots turn the masks of a row into its bit planes.
+// INTERIOR tiles (no volume boundary within reach) skip all validity logic.
 template <typename L, int MODE, bool INTERIOR>
-__device__ __forceinline__ bool scan_tile(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const L* lab,
+__device__ __forceinline__ bool scan_tile(const VolParams& vp, P1Smem<L, MODE>& S, const L* lab,
                                           uint32_t ef0, uint32_t em0, uint32_t es0) {
   constexpr int RFP = P1Smem<L, MODE>::RFP;
   constexpr uint32_t FULL = 0xffffffffu;
@@ -321,7 +397,6 @@ __device__ __forceinline__ bool scan_tile(const VolParams& vp, const Pass1Args& 
   bool nef = a != af, nes = a != as_;
   bool eq_row = !nef && !nes && a == p[RM * RFP + 1];  // the 4 corners of row j agree
   bool za = a != 0, zf = af != 0, zs = as_ != 0;
-  uint8_t* orow = o.own6 + ((size_t)es * vp.Em + em0) * vp.Efp + ef;
   bool any = false;
 #pragma unroll
   for (int j = 0; j < TM; ++j) {
@@ -347,24 +422,29 @@ __device__ __forceinline__ bool scan_tile(const VolParams& vp, const Pass1Args& 
       act = (m != 0u) || (valid && nf1 && nm1 && ns1 && !uniform);
     }
     const uint32_t ab = __ballot_sync(FULL, act);
-    uint32_t rowtotal = 0;
-    if (ab) {
+    if (ab) {  // (m != 0 implies act, so rows without active voxels keep their cleared planes)
       any = true;
       if (INTERIOR) {
         if (nef) m |= (za ? 1u : 0u) | (zf ? 2u : 0u);
         if (nem) m |= (za ? 4u : 0u) | (zm ? 8u : 0u);
         if (nes) m |= (za ? 16u : 0u) | (zs ? 32u : 0u);
       }
-      uint32_t pre = 0;
-      if (__ballot_sync(FULL, m != 0u)) pre = warp_prefix3(__popc(m), ltm, rowtotal);
+      if (__ballot_sync(FULL, m != 0u)) {
+        const uint32_t b0 = __ballot_sync(FULL, m & 1u), b1 = __ballot_sync(FULL, m & 2u);
+        const uint32_t b2 = __ballot_sync(FULL, m & 4u), b3 = __ballot_sync(FULL, m & 8u);
+        const uint32_t b4 = __ballot_sync(FULL, m & 16u), b5 = __ballot_sync(FULL, m & 32u);
+        if (lane == 0) {
+          uint32_t* row = S.pl[ls * TM + j];
+          *reinterpret_cast<uint4*>(row) = make_uint4(b0, b1, b2, b3);
+          *reinterpret_cast<uint4*>(row + 4) =
+              make_uint4(b4, b5, __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3) + __popc(b4) + __popc(b5), 0u);
+        }
+      }
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(&S.nact, (uint32_t)__popc(ab));
       base = __shfl_sync(FULL, base, 0);
-      if (act) S.alist[base + __popc(ab & ltm)] = (uint32_t)((ls * TM + j) * TF + lane) | (m << 11) | (pre << 17);
+      if (act) S.alist[base + __popc(ab & ltm)] = (uint32_t)((ls * TM + j) * TF + lane) | (m << 11);
     }
-    if (okm && oks) *orow = (uint8_t)m;
-    orow += vp.Efp;
-    if (lane == 0) S.rowcnt[ls * TM + j] = rowtotal;
     a = am; af = amf; as_ = ams;
     nef = nef2; nes = nes2; eq_row = eq_row2;
     za = zm; zf = amf != 0; zs = ams != 0;
@@ -372,74 +452,46 @@ __device__ __forceinline__ bool scan_tile(const VolParams& vp, const Pass1Args& 
   return any;
 }
 
+// clear the per-tile tables (all threads; caller synchronises)
+template <typename L, int MODE>
+__device__ __forceinline__ void clear_tables(P1Smem<L, MODE>& S) {
+  constexpr int LT = Caps<MODE>::LT;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
+  uint4* plq = reinterpret_cast<uint4*>(&S.pl[0][0]);
+  for (int i = tid; i < NROWS * RI_WORDS / 4; i += NT) plq[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) { S.nact = 0; S.nrec = 0; S.nlab = 0; S.overflow = 0; S.ci = 0; S.ttot = 0; }
+}
+
+enum : int { TILE_EMPTY = 0, TILE_DEFERRED = 1, TILE_ACTIVE = 2 };
+
+// S1-S3 of a (half) tile: everything that reads the staged labels.  Ends with a barrier after
+// which the region is dead.  Planes [h0, h0 + nh) of the tile are processed (all 8 in MODE 0).
 template <typename L, bool CO, int MODE>
-__device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtensorMap* tmap, const Pass1Args& o,
-                                              P1Smem<L, MODE>& S, const uint32_t tile, uint32_t& parity) {
+__device__ __forceinline__ int tile_front(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const uint32_t tile,
+                                          const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh) {
   constexpr int RFP = P1Smem<L, MODE>::RFP;
   constexpr int LT = Caps<MODE>::LT, VCAP = Caps<MODE>::VCAP, RCAP = Caps<MODE>::RCAP, PROBES = Caps<MODE>::PROBES;
   constexpr uint32_t FULL = 0xffffffffu;
+  constexpr int ALIGN = 16 / (int)sizeof(L);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ltm = (1u << lane) - 1u;
-
-  uint32_t b = tile;
-  const uint32_t tf = b % vp.ntf;
-  b /= vp.ntf;
-  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
   const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
+  const L* const lab = S.lab + (vp.pad ? ALIGN - 1 : 0);
 
-  // ---- S0: stage the label region; clear the tile tables meanwhile ----
-  // TMA needs a 16-byte aligned start along f: with the `close` border the box starts ALIGN
-  // elements (not 1) before the tile and the region sits `coff` columns into the staged rows.
-  constexpr int ALIGN = 16 / (int)sizeof(L);
-  const int coff = vp.pad ? ALIGN - 1 : 0;
-  L* const lab = S.lab + coff;
-  if (vp.use_tma) {
-    if (tid == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(&S.mbar, (uint32_t)(sizeof(L) * RS * RM * RFP));
-      tma_load_3d(S.lab, tmap, &S.mbar, (int)ef0 - (vp.pad ? ALIGN : 0), (int)em0 - (int)vp.pad, (int)es0 + vp.s_shift);
-      if (MODE == 0) {  // pull the tile a later CTA will stage into L2 now
-        uint32_t pt = tile + PREFETCH_DISTANCE;
-        if (pt < vp.ntf * vp.ntm * vp.nts) {
-          const uint32_t ptf = pt % vp.ntf;
-          pt /= vp.ntf;
-          tma_prefetch_3d(tmap, (int)(ptf * TF) - (vp.pad ? ALIGN : 0), (int)((pt % vp.ntm) * TM) - (int)vp.pad,
-                          (int)((pt / vp.ntm) * TS) + vp.s_shift);
-        }
-      }
-    }
-  } else {
-    const L* __restrict__ src = static_cast<const L*>(vp.data);
-    for (int i = tid; i < (TF + 1) * RM * RS; i += NT) {
-      const int lf = i % (TF + 1);
-      const int t = i / (TF + 1);
-      const int lm = t % RM, ls = t / RM;
-      const uint32_t jf = ef0 + lf - vp.pad, jm = em0 + lm - vp.pad, js = es0 + ls + (uint32_t)vp.s_shift;  // wraps when < 0
-      L v = 0;
-      if (jf < vp.nf && jm < vp.nm && js < vp.ns) v = src[((size_t)js * vp.nm + jm) * vp.nf + jf];
-      lab[(ls * RM + lm) * RFP + lf] = v;
-    }
+  // ---- S1: slot masks -> bit planes, compaction of active voxels ----
+  bool any = false;
+  if (warp >= h0 && warp < h0 + nh) {
+    if (ef0 + TF + 1 <= vp.Ef && em0 + TM + 1 <= vp.Em && es0 + TS + 1 <= vp.Es)
+      any = scan_tile<L, MODE, true>(vp, S, lab, ef0, em0, es0);
+    else
+      any = scan_tile<L, MODE, false>(vp, S, lab, ef0, em0, es0);
   }
-  S.tricount[tid] = TRI_COUNT_D[tid];
-  for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
-  if (tid == 0) { S.nact = 0; S.nrec = 0; S.nlab = 0; S.overflow = 0; S.ci = 0; S.ttot = 0; }
-  __syncthreads();  // mbarrier initialised, tables cleared, (plain-load path) region staged
-  if (vp.use_tma) {
-    mbar_wait(&S.mbar, parity);  // every thread waits itself: the TMA writes are visible to it afterwards
-    parity ^= 1u;
-  }
+  if (!__syncthreads_or(any ? 1 : 0)) return TILE_EMPTY;
 
-  // ---- S1: slot masks, in-row prefixes, compaction of active voxels ----
-  bool any;
-  if (ef0 + TF + 1 <= vp.Ef && em0 + TM + 1 <= vp.Em && es0 + TS + 1 <= vp.Es)
-    any = scan_tile<L, MODE, true>(vp, o, S, lab, ef0, em0, es0);
-  else
-    any = scan_tile<L, MODE, false>(vp, o, S, lab, ef0, em0, es0);
-  if (!__syncthreads_or(any ? 1 : 0)) return;  // uniform tile: nothing but the own6 zeros
-
-  // ---- S2: row bases inside the tile ----
+  // ---- S2: first slot of every row and of every (row, plane) inside the tile ----
   if (warp == 0) {
-    const uint32_t a0 = S.rowcnt[2 * lane], a1 = S.rowcnt[2 * lane + 1];
+    const uint32_t a0 = S.pl[2 * lane][6], a1 = S.pl[2 * lane + 1][6];
     const uint32_t sum = a0 + a1;
     uint32_t inc = sum;
 #pragma unroll
@@ -447,15 +499,24 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
       uint32_t t = __shfl_up_sync(FULL, inc, d);
       if (lane >= d) inc += t;
     }
-    S.rowpre[2 * lane] = inc - sum;
-    S.rowpre[2 * lane + 1] = inc - sum + a0;
     if (lane == 31) S.nslots = inc;
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      uint32_t* row = S.pl[2 * lane + r];
+      row[6] = run;
+#pragma unroll
+      for (int s = 0; s < 6; ++s) {
+        S.pp[2 * lane + r][s] = (uint16_t)run;
+        run += __popc(row[s]);
+      }
+    }
   }
   __syncthreads();
   const uint32_t nslots = S.nslots, nact = S.nact;
   if (MODE == 0 && nslots > (uint32_t)VCAP) {
     if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
-    return;
+    return TILE_DEFERRED;
   }
 
   // ---- S3: per active voxel: distinct labels of its cube -> counts, local ranks, records ----
@@ -471,7 +532,8 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
       c[n] = lab[((ls + corner_ds<CO>(n)) * RM + (lm + corner_dm<CO>(n))) * RFP + (lf + corner_df<CO>(n))];
     const uint32_t m = (aw >> 11) & 63u;
     const bool cube = (ef0 + lf + 1 < vp.Ef) && (em0 + lm + 1 < vp.Em) && (es0 + ls + 1 < vp.Es);
-    const uint32_t gl0 = S.rowpre[vidx >> 5] + (aw >> 17);
+    const uint32_t row = vidx >> 5;
+    const uint32_t ltf = (1u << lf) - 1u;
     uint32_t acc = valid ? 0u : 0xFFu;
     while (__any_sync(FULL, acc != 0xFFu)) {
       const bool have = acc != 0xFFu;
@@ -499,11 +561,12 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
         if (hs < 0) { S.overflow = 1u; work = false; }
       }
       // warp-aggregated add of (nv | nt << 16) to lcnt[hs]; the return value ranks the vertices
+      // and gives the record its first face row inside the (tile,label) block
       const uint32_t grp = __match_any_sync(FULL, work ? (uint32_t)hs : 0xFFFFFFFFu);
       const uint32_t glt = grp & ltm;
       uint32_t totv, tott;
       const uint32_t prev = group_prefix3(work ? nv : 0u, grp, glt, totv);
-      (void)group_prefix3(work ? nt : 0u, grp, glt, tott);
+      const uint32_t pret = group_prefix3(work ? nt : 0u, grp, glt, tott);
       const int leader = __ffs(grp) - 1;
       uint32_t old = 0;
       if (work && lane == leader) old = atomicAdd(&S.lcnt[hs], totv | (tott << 16));
@@ -514,7 +577,7 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
         while (mm) {
           const int s6 = __ffs(mm) - 1;
           mm &= mm - 1u;
-          const uint32_t lg = gl0 + __popc(m & ((1u << s6) - 1u));
+          const uint32_t lg = (uint32_t)S.pp[row][s6] + __popc(S.pl[row][s6] & ltf);
           S.vstage[lg] = (r << 12) | (uint32_t)hs;
           S.pstage[lg] = (uint16_t)(vidx | ((uint32_t)s6 << 11));
           ++r;
@@ -528,21 +591,36 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
         rbase = __shfl_sync(FULL, rbase, 0);
         if (hasrec) {
           const uint32_t pos = rbase + __popc(rb & ltm);
-          if (pos < (uint32_t)RCAP) S.rstage[pos] = vidx | (cs << 11) | ((uint32_t)hs << 19);
-          else S.overflow = 1u;
+          if (pos < (uint32_t)RCAP) {
+            S.rstage[pos] = vidx | (cs << 11) | ((uint32_t)hs << 19);
+            S.rtoff[pos] = (uint16_t)((old >> 16) + pret);
+          } else {
+            S.overflow = 1u;
+          }
         }
       }
     }
   }
   __syncthreads();
-  if (MODE == 0 && S.overflow) {
-    if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
-    return;
+  if (S.overflow) {
+    if (MODE == 0) {
+      if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
+    } else {
+      if (tid == 0) atomicOr(&o.ctl->flags, FLAG_INTERNAL);
+    }
+    return TILE_DEFERRED;
   }
-  if (MODE == 1 && S.overflow) {
-    if (tid == 0) atomicOr(&o.ctl->flags, FLAG_INTERNAL);
-    return;
-  }
+  return TILE_ACTIVE;
+}
+
+// S5-S6 of a (half) tile: reservations and the coalesced flush.  Does not touch the staged labels.
+template <typename L, int MODE>
+__device__ __forceinline__ void tile_back(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const uint32_t tile,
+                                          const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh) {
+  constexpr int LT = Caps<MODE>::LT;
+  constexpr uint32_t FULL = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t nslots = S.nslots;
 
   // ---- S5: reserve the tile's segments and the per-label ranges ----
   {
@@ -602,11 +680,18 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
   }
   __syncthreads();
 
-  // ---- S6: flush rowbase, perm/vl and the records (coalesced) ----
+  // ---- S6: flush rowinfo, perm/vinfo and the records (coalesced) ----
   if (tid == 0 && S.ttot) atomicAdd(&o.ctl->cur_tri, (u64)S.ttot);
-  if (tid < TM * TS) {
-    const uint32_t rs = es0 + tid / TM, rm = em0 + tid % TM;
-    if (rs < vp.Es_own && rm < vp.Em) o.rowbase[((size_t)rs * vp.Em + rm) * vp.ntf + tf] = gbase + S.rowpre[tid];
+  {
+    const int row = tid >> 2, q = tid & 3;  // 4 threads per row segment, 8 bytes each
+    if (row >= h0 * TM && row < (h0 + nh) * TM) {
+      const uint32_t rs = ts * TS + row / TM, rm = tm * TM + row % TM;
+      if (rs < vp.Es_own && rm < vp.Em) {
+        uint2 w = *reinterpret_cast<const uint2*>(&S.pl[row][2 * q]);
+        if (q == 3) { w.x += gbase; w.y = 0u; }
+        reinterpret_cast<uint2*>(o.rowinfo + (((size_t)rs * vp.Em + rm) * vp.ntf + tf) * RI_WORDS)[q] = w;
+      }
+    }
   }
   for (uint32_t i = tid; i < nslots; i += NT) {
     const uint32_t w = S.vstage[i];
@@ -617,26 +702,99 @@ __device__ __forceinline__ void classify_tile(const VolParams& vp, const CUtenso
   const uint32_t nrec = S.nrec;
   for (uint32_t i = tid; i < nrec; i += NT) {
     const uint32_t w = S.rstage[i];
-    o.rec[recbase + i] = (w & 0x7FFFFu) | ((uint32_t)S.cidx[w >> 19] << 19);
+    o.rec[recbase + i] = (u64)((w & 0x7FFFFu) | ((uint32_t)S.cidx[w >> 19] << 19)) | ((u64)S.rtoff[i] << 32);
   }
 }
 
+// MODE 0: persistent CTAs, tile t -> CTA t mod gridDim.  One label buffer per CTA: the load of the
+// next tile is issued the moment the current region is dead (after the uniform test of a uniform
+// tile, after S3 of an active one) and overlaps the flush.  MODE 1: the queued dense tiles.
 template <typename L, bool CO, int MODE>
-__global__ void __launch_bounds__(NT) k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(NT, MODE == 0 ? 4 : 1) k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap,
                                                  const Pass1Args o) {
   P1Smem<L, MODE>& S = *reinterpret_cast<P1Smem<L, MODE>*>(zm_dyn_smem);
-  if (threadIdx.x == 0) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
     mbar_init(&S.mbar, 1);
     fence_mbar_init();
   }
+  S.tricount[tid] = TRI_COUNT_D[tid];
+  clear_tables(S);
   uint32_t parity = 0;
   if (MODE == 0) {
-    classify_tile<L, CO, MODE>(vp, &tmap, o, S, blockIdx.x, parity);
+    const uint32_t ntiles = vp.ntf * vp.ntm * vp.nts;
+    uint32_t tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    if (tid == 0) {
+      publish_tile(vp, S, tile, 0);
+      if (vp.use_tma) issue_tile(vp, &tmap, S, 0);
+    }
+    __syncthreads();
+    bool dirty = false;
+    for (uint32_t it = 0; tile < ntiles; ++it) {
+      const uint32_t next = tile + gridDim.x;
+      const int cur = it & 1;
+      const uint32_t tf = S.tc[cur][0], tm = S.tc[cur][1], ts = S.tc[cur][2];
+      if (tid == 0 && next < ntiles) publish_tile(vp, S, next, cur ^ 1);
+      if (vp.use_tma) {
+        mbar_wait(&S.mbar, parity);  // every thread waits itself: the TMA writes are visible to it afterwards
+        parity ^= 1u;
+      } else {
+        stage_plain(vp, S, tf, tm, ts);
+        __syncthreads();
+      }
+      int status = TILE_EMPTY;
+      if (!region_uniform(S)) {
+        if (dirty) {
+          clear_tables(S);
+          __syncthreads();
+          dirty = false;
+        }
+        status = tile_front<L, CO, MODE>(vp, o, S, tile, tf, tm, ts, 0, TS);
+        dirty = true;
+      }
+      // the staged region is dead (every path above ends with a barrier): fetch the next one
+      if (tid == 0 && vp.use_tma && next < ntiles) issue_tile(vp, &tmap, S, cur ^ 1);
+      if (status == TILE_EMPTY) zero_rows(vp, o, tf, tm, ts);
+      else if (status == TILE_ACTIVE) tile_back<L, MODE>(vp, o, S, tile, tf, tm, ts, 0, TS);
+      if (!vp.use_tma || status != TILE_EMPTY) __syncthreads();
+      tile = next;
+    }
   } else {
     const uint32_t n = o.ctl->dense_count;  // written by the MODE 0 launch that precedes this one
+    __syncthreads();
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-      classify_tile<L, CO, MODE>(vp, &tmap, o, S, o.dense_list[i], parity);
+      const uint32_t tile = o.dense_list[i];
+      if (tid == 0) {
+        publish_tile(vp, S, tile, 0);
+        if (vp.use_tma) issue_tile(vp, &tmap, S, 0);
+      }
       __syncthreads();
+      const uint32_t tf = S.tc[0][0], tm = S.tc[0][1], ts = S.tc[0][2];
+      if (vp.use_tma) {
+        mbar_wait(&S.mbar, parity);
+        parity ^= 1u;
+      } else {
+        stage_plain(vp, S, tf, tm, ts);
+        __syncthreads();
+      }
+      for (int half = 0; half < Caps<MODE>::HALVES; ++half) {
+        const int nh = TS / Caps<MODE>::HALVES, h0 = half * nh;
+        if (i != blockIdx.x || half != 0) clear_tables(S);
+        __syncthreads();
+        const int status = tile_front<L, CO, MODE>(vp, o, S, tile, tf, tm, ts, h0, nh);
+        if (status == TILE_ACTIVE) tile_back<L, MODE>(vp, o, S, tile, tf, tm, ts, h0, nh);
+        else if (status == TILE_EMPTY) {
+          // rows of this half without slots
+          const int row = tid >> 1;
+          if (tid < 2 * NROWS && row >= h0 * TM && row < (h0 + nh) * TM) {
+            const uint32_t rs = ts * TS + row / TM, rm = tm * TM + row % TM;
+            if (rs < vp.Es_own && rm < vp.Em)
+              reinterpret_cast<uint4*>(o.rowinfo + (((size_t)rs * vp.Em + rm) * vp.ntf + tf) * RI_WORDS)[tid & 1] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        __syncthreads();
+      }
     }
   }
 }
@@ -791,19 +949,18 @@ __global__ void __launch_bounds__(256) k_set_voff(const LabelTable ht, const u64
 
 struct Pass2Args {
   const TileHdr* hdr;
-  const uint8_t* own6;
-  const uint32_t* rowbase;
   const uint32_t* perm;
   const uint32_t* vinfo;
-  const uint32_t* rec;
+  const u64* rec;
   const TLEntry* tl;
   uint32_t* faces;  // [T_total][3]
   float* verts;     // [V_total][3]
   float* normals;   // [V_total][3] or null
   float r0, r1, r2;  // captured resolution
   float c0, c1, c2;  // centering offset
+  uint32_t n_work;
   int voxel_centered, transpose;
-  int write_faces, write_verts, normalize;
+  int write_faces, write_verts;
   const uint32_t* foreign;  // slab sharding: final indices of the top plane's slots, [Em][Efp][4], from the next shard
 };
 
@@ -838,28 +995,6 @@ __device__ __forceinline__ void face_normal_scatter(const float v0[3], const flo
   }
 }
 
-// The contribution of one face to ONE of its corners (same arithmetic as face_normal_scatter).
-__device__ __forceinline__ void face_normal_corner(const float v0[3], const float v1[3], const float v2[3], int k,
-                                                   float* dst) {
-  float c[3], e1[3], e2[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    c[d] = __fdiv_rn(__fadd_rn(__fadd_rn(v0[d], v1[d]), v2[d]), 3.0f);
-    e1[d] = __fsub_rn(v1[d], v0[d]);
-    e2[d] = __fsub_rn(v2[d], v0[d]);
-  }
-  float n0 = __fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1]));
-  float n1 = __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2]));
-  float n2 = __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0]));
-  const float l = len3(n0, n1, n2);
-  if (l != 1.0f) { n0 = __fdiv_rn(n0, l); n1 = __fdiv_rn(n1, l); n2 = __fdiv_rn(n2, l); }
-  const float* vk = k == 0 ? v0 : (k == 1 ? v1 : v2);
-  const float w = len3(__fsub_rn(vk[0], c[0]), __fsub_rn(vk[1], c[1]), __fsub_rn(vk[2], c[2]));
-  atomicAdd(dst + 0, __fmul_rn(n0, w));
-  atomicAdd(dst + 1, __fmul_rn(n1, w));
-  atomicAdd(dst + 2, __fmul_rn(n2, w));
-}
-
 // p = res * k for the vertex on the edge of memory axis d owned by extended voxel (ef, em, es):
 // half-voxel key, memory axes -> logical axes, + shard origin (reference: unpack_*,
 // marching_cubes.hpp:114-135 with offset 0, factor = captured resolution; transpose = the legacy
@@ -875,29 +1010,33 @@ __device__ __forceinline__ void slot_position(const VolParams& vp, const Pass2Ar
   else             { p0 = __fmul_rn(a.r0, kx); p1 = __fmul_rn(a.r1, ky); p2 = __fmul_rn(a.r2, kz); }
 }
 
-// per (case, output corner) of the triangle table: region index delta of the owner voxel (9 bits) |
-// slot << 9 | owner offset (f,m,s) << 12; rows of 16 entries, triangle t at [3t, 3t+3) in the
-// reference winding of Mesher.get: (E[T[3n+1]], E[T[3n]], E[T[3n+2]])
-// (marching_cubes.hpp:338-343 then cMesher.hpp:158-162).  Filled by prepare_device.
-__device__ __align__(16) uint16_t CASE_TAB_D[2][256 * 16];
+// per (case, triangle): three bytes, one per output corner, in the reference winding of Mesher.get:
+// (E[T[3n+1]], E[T[3n]], E[T[3n+2]])  (marching_cubes.hpp:338-343 then cMesher.hpp:158-162).
+// Byte: row delta of the owner voxel (ds * RM + dm, 4 bits) | its f offset << 4 | slot << 5.
+// Filled by prepare_device.
+constexpr int CASE_TRIS = 5;
+__device__ __align__(16) uint32_t CASE_TAB_D[2][256 * CASE_TRIS];
 
 template <bool CO>
-inline void build_case_table(uint16_t* tab) {
+inline void build_case_table(uint32_t* tab) {
   uint32_t info[12];
   for (int e = 0; e < 12; ++e) info[e] = edge_info<CO>(e);
   static const int order[3] = {1, 0, 2};
   for (int cs = 0; cs < 256; ++cs)
-    for (int t = 0; t < 5; ++t)
+    for (int t = 0; t < CASE_TRIS; ++t) {
+      uint32_t w = 0;
       for (int k = 0; k < 3; ++k) {
         const int ed = (int)((TRI_NIBBLES[cs] >> (12 * t + 4 * order[k])) & 0xFull);
-        uint16_t v = 0;
+        uint32_t v = 0;
         if (t < TRI_COUNT[cs] && ed < 12) {
           const uint32_t i = info[ed];
           const uint32_t slot = ((i >> 12) & 7u) + (((uint32_t)cs >> ((i >> 16) & 7u)) & 1u);
-          v = (uint16_t)((i & 0x1FFu) | (slot << 9) | (((i >> 20) & 7u) << 12));
+          v = (i & 0x1Fu) | (slot << 5);
         }
-        tab[cs * 16 + 3 * t + k] = v;
+        w |= v << (8 * k);
       }
+      tab[cs * CASE_TRIS + t] = w;
+    }
 }
 
 __device__ __forceinline__ TileHdr load_hdr(const TileHdr* p) {
@@ -907,197 +1046,195 @@ __device__ __forceinline__ TileHdr load_hdr(const TileHdr* p) {
   return u.h;
 }
 
-// faces: one CTA per non-empty tile.  Records are read 32 per warp; their triangles are expanded
-// into (triangle, corner) items so that every lane does exactly one vertex lookup and one 4-byte
-// store, consecutive lanes writing consecutive words of the face array.
-constexpr int FW = 48;  // row pitch of the staged own6 region: 32 voxels + the halo voxel, 16-byte aligned rows (cp.async)
+// k_emit: persistent CTAs over the work list of non-empty (half) tiles.  Per tile one TMA load
+// brings the rowinfo of the (TM+1)(TS+1) rows x 2 segments whose slots the tile's cubes can
+// reference (the load of the CTA's next tile is in flight meanwhile); 162 threads turn it into
+// per-(row, segment, plane) slot bases.  Records are read 32 per warp, their triangles expanded so
+// that every lane owns one triangle: three slot lookups (two shared loads + popc -> perm) and three
+// 4-byte stores, consecutive lanes writing consecutive 12-byte rows.  Then one thread per vertex
+// slot of the tile writes the float32 vertex in its final form (reference: _normalize_mesh
+// zmesh/_zmesh.pyx:423-433: three separately rounded float32 operations, no FMA).
+constexpr int RGN_ROWS = RM * RS;            // 81
+constexpr int RGN_WORDS = 2 * RI_WORDS;      // two row segments per region row
+constexpr int RGN_PAD = 1312;                // words per staged region buffer (5184 B rounded up to 128 B)
+constexpr int TLC = 64;                      // tile-local labels whose tl entry is cached in shared memory
 template <bool CO, bool NORMALS, bool SLAB>
-__global__ void __launch_bounds__(NT, NORMALS ? 4 : 5) k_faces(const VolParams vp, const Pass2Args a) {
+__global__ void __launch_bounds__(NT, NORMALS ? 3 : 4) k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap,
+                                                             const Pass2Args a) {
   constexpr uint32_t FULL = 0xffffffffu;
-  constexpr int NROW = RM * RS;                   // 81 rows of TF+1 voxels
-  __shared__ uint32_t gb[NROW * FW];      // spatial id of the first slot of each region voxel
-  __shared__ __align__(16) uint8_t o6[NROW * FW];
-  __shared__ uint32_t rbs[NROW][2];       // row bases: this tile column, next tile column
-  __shared__ uint32_t cur[Caps<1>::LT / 2];  // running face cursors per tile-local label, two 16-bit halves per word
-  __shared__ __align__(16) uint16_t s_tab[256 * 16];
+  __shared__ __align__(128) uint32_t R[2][RGN_PAD];   // TMA destinations: rowinfo of the region
+  __shared__ uint32_t rb[RGN_ROWS * RGN_WORDS];       // spatial id of the first slot of (row, segment, plane)
+  __shared__ __align__(16) TLEntry tls[TLC];
+  __shared__ __align__(16) TileHdr s_hdr[2];
+  __shared__ u64 bar[2];
+  __shared__ uint32_t s_tab[256 * CASE_TRIS];
   __shared__ uint8_t s_tricount[256];
   __shared__ u64 rf[NW][32];              // per record of the warp's batch: first face row
   __shared__ u64 rv[NW][32];              //                                  first vertex row of the label
-  __shared__ uint32_t ru[NW][32];         //                                  region index | case << 16
+  __shared__ uint32_t ru[NW][32];         //                                  region row | f << 8 | case << 16
   __shared__ uint32_t rvo[NW][32];        //                                  index offset of the label (earlier shards)
   __shared__ uint8_t tlist[NW][160];      // triangles of the batch: record lane << 3 | t
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ltm = (1u << lane) - 1u;
-  const TileHdr h = load_hdr(a.hdr + blockIdx.x);
-  if (h.nrec == 0) return;
-  uint32_t b = h.tile;
-  const uint32_t tf = b % vp.ntf;
-  b /= vp.ntf;
-  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
-  const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
+  const uint32_t n = a.n_work, G = gridDim.x;
+  uint32_t i = blockIdx.x;
+  if (i >= n) return;
 
-  // own6 of the (TF+1)(TM+1)(TS+1) voxels whose slots the tile's cubes can reference and the
-  // spatial id of each voxel's first slot; all loads of a warp are issued before any is used
+  auto issue = [&](const TileHdr& h, int buf) {  // thread 0
+    uint32_t b = h.tile;
+    const uint32_t tf = b % vp.ntf;
+    b /= vp.ntf;
+    const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
+    fence_proxy_async();
+    mbar_expect_tx(&bar[buf], (uint32_t)(RGN_ROWS * RGN_WORDS * 4));
+    tma_load_3d(R[buf], &rmap, &bar[buf], (int)(tf * RI_WORDS), (int)(tm * TM), (int)(ts * TS));
+  };
+
+  TileHdr hnext;
+  hnext.tile = 0;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+    const TileHdr h0 = load_hdr(a.hdr + i);
+    s_hdr[0] = h0;
+    issue(h0, 0);
+    if (i + G < n) hnext = load_hdr(a.hdr + i + G);
+  }
   s_tricount[tid] = TRI_COUNT_D[tid];
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(CASE_TAB_D[CO ? 1 : 0]);
-    uint4* dst = reinterpret_cast<uint4*>(s_tab);
-    dst[tid] = src[tid];
-    dst[tid + NT] = src[tid + NT];
-  }
-  for (uint32_t i = tid; i < (h.nlab + 1u) / 2u; i += NT) cur[i] = 0u;
-  // stage the own6 bytes of the (TF+1)(TM+1)(TS+1) voxels whose slots the tile's cubes can reference
-  // and the row bases with cp.async (LDGSTS): 2 x 16 B + 4 B (halo voxel = first voxel of the next
-  // tile's row) + 2 x 4 B per row, no register staging
-  {
-    const bool more = tf + 1 < vp.ntf;
-    for (int i = tid; i < 5 * NROW; i += NT) {
-      const int r = i / 5, part = i - 5 * r;
-      const int ls = r / RM, lm = r - ls * RM;
-      const uint32_t em = em0 + lm, es = es0 + ls;
-      const bool rowvalid = em < vp.Em && es < vp.Es_own;
-      const size_t row = (size_t)es * vp.Em + em;
-      if (part < 2) {
-        if (rowvalid) cp_async<16>(&o6[r * FW + 16 * part], a.own6 + row * vp.Efp + ef0 + 16 * part);
-        else *reinterpret_cast<uint4*>(&o6[r * FW + 16 * part]) = make_uint4(0u, 0u, 0u, 0u);
-      } else if (part == 2) {
-        if (rowvalid && more) cp_async<4>(&o6[r * FW + TF], a.own6 + row * vp.Efp + ef0 + TF);
-        else *reinterpret_cast<uint32_t*>(&o6[r * FW + TF]) = 0u;
-      } else {
-        const int c = part - 3;
-        if (rowvalid && (c == 0 || more)) cp_async<4>(&rbs[r][c], a.rowbase + row * vp.ntf + tf + c);
-        else rbs[r][c] = 0u;
-      }
-    }
-    cp_async_wait_all();
-  }
-  __syncthreads();
-  // spatial id of each region voxel's first slot (only rows that have slots need it)
-  for (int r = warp; r < NROW; r += NW) {
-    const int ls = r / RM, lm = r - ls * RM;
-    if (SLAB && es0 + ls == vp.Es_own && vp.Es_own < vp.Es) {
-      // top plane of a slab: its slots belong to the next shard; look them up in a.foreign
-      const uint32_t fbase = 0x80000000u | ((em0 + lm) * vp.Efp + ef0);
-      gb[r * FW + lane] = fbase + lane;
-      if (lane == 0) gb[r * FW + TF] = fbase + TF;
-      continue;
-    }
-    const uint32_t m = o6[r * FW + lane];
-    if (__ballot_sync(FULL, m != 0u)) {
-      uint32_t rowtotal;
-      const uint32_t pre = warp_prefix3(__popc(m), ltm, rowtotal);
-      gb[r * FW + lane] = rbs[r][0] + pre;
-    }
-    if (lane == 0) gb[r * FW + TF] = rbs[r][1];
-  }
+  for (int j = tid; j < 256 * CASE_TRIS; j += NT) s_tab[j] = CASE_TAB_D[CO ? 1 : 0][j];
   __syncthreads();
 
-  const uint32_t nrec = h.nrec;
-  for (uint32_t base = warp * 32; base < nrec; base += NT) {
-    const uint32_t i = base + lane;
-    const bool valid = i < nrec;
-    const uint32_t w = valid ? __ldg(a.rec + h.recbase + i) : 0u;
-    const uint32_t vidx = w & 0x7FFu, cs = (w >> 11) & 0xFFu, ci = w >> 19;
-    const uint32_t nt = valid ? s_tricount[cs] : 0u;
-    // warp-aggregated reservation of nt face rows in the (tile,label) block
-    const uint32_t grp = __match_any_sync(FULL, valid ? ci : 0xFFFFFFFFu);
-    uint32_t tot;
-    const uint32_t pre = group_prefix3(nt, grp, grp & ltm, tot);
-    const int leader = __ffs(grp) - 1;
-    const uint32_t sh = (ci & 1u) * 16u;
-    uint32_t old = 0;
-    if (valid && lane == leader) old = atomicAdd(&cur[ci >> 1], tot << sh);
-    old = (__shfl_sync(FULL, old, leader) >> sh) & 0xFFFFu;
-    uint32_t ntot;
-    const uint32_t tpre = warp_prefix3(nt, ltm, ntot);
-    if (valid) {
-      const TLEntry e = a.tl[h.tlbase + ci];
-      const uint32_t lf = vidx & 31u, lm = (vidx >> 5) & 7u, ls = vidx >> 8;
-      ru[warp][lane] = ((ls * RM + lm) * FW + lf) | (cs << 16);
-      rf[warp][lane] = e.b + old + pre;
-      if (SLAB) rvo[warp][lane] = (uint32_t)(e.a >> 32);
-      if (NORMALS) rv[warp][lane] = e.a & 0xFFFFFFFFull;
-      for (uint32_t t = 0; t < nt; ++t) tlist[warp][tpre + t] = (uint8_t)((lane << 3) | t);
+  for (uint32_t it = 0; i < n; i += G, ++it) {
+    const int cur = it & 1;
+    if (tid == 0 && i + G < n) {
+      s_hdr[cur ^ 1] = hnext;
+      issue(hnext, cur ^ 1);
+      if (i + 2 * G < n) hnext = load_hdr(a.hdr + i + 2 * G);
     }
-    __syncwarp();
-    for (uint32_t j = lane; j < 3u * ntot; j += 32) {
-      const uint32_t q = (j * 171u) >> 9;  // j / 3 for j < 512
-      const uint32_t k = j - 3u * q;
-      const uint32_t tr = tlist[warp][q];
-      const uint32_t src = tr >> 3, t = tr & 7u;
-      const uint32_t uc = ru[warp][src];
-      const uint32_t u0 = uc & 0xFFFFu, rcs = uc >> 16;
-      const uint16_t* tab = s_tab + rcs * 16 + 3u * t;
-      const uint32_t en = tab[k];
-      const uint32_t u = u0 + (en & 0x1FFu);
-      // slot = 2*axis + side; side 0: the owner (lower) voxel carries the label, 1: the upper one
-      const uint32_t slot = (en >> 9) & 7u;
-      const uint32_t gv = gb[u];
-      uint32_t vi;
-      if (SLAB && (gv & 0x80000000u)) vi = __ldg(a.foreign + 4ull * (gv & 0x7FFFFFFFu) + slot);
-      else vi = __ldg(a.perm + gv + __popc((uint32_t)o6[u] & ((1u << slot) - 1u))) + (SLAB ? rvo[warp][src] : 0u);
-      if (a.write_faces) a.faces[3ull * (rf[warp][src] + t) + k] = vi;
-      if (NORMALS) {
-        // the lane owning corner k recomputes the face normal from the cube geometry (no loads)
-        const uint32_t ls = u0 / (RM * FW), rem = u0 - ls * (RM * FW), lm = rem / FW, lf = rem - lm * FW;
-        float p[3][3];
+    TileHdr h;
+    {
+      union { uint4 q[2]; TileHdr h; } u;
+      u.q[0] = reinterpret_cast<const uint4*>(&s_hdr[cur])[0];
+      u.q[1] = reinterpret_cast<const uint4*>(&s_hdr[cur])[1];
+      h = u.h;
+    }
+    uint32_t b = h.tile;
+    const uint32_t tf = b % vp.ntf;
+    b /= vp.ntf;
+    const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
+    const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
+    const uint32_t* Rc = R[cur];
+    // slab sharding: region rows [ftop9, ftop9 + RM) lie on the plane owned by the next shard
+    uint32_t ftop9 = 0xFFFFu;
+    if (SLAB && vp.Es_own < vp.Es && vp.Es_own >= es0 && vp.Es_own - es0 < (uint32_t)RS) ftop9 = (vp.Es_own - es0) * RM;
+
+    for (uint32_t j = tid; j < h.nlab && j < (uint32_t)TLC; j += NT) tls[j] = a.tl[h.tlbase + j];
+    mbar_wait(&bar[cur], (it >> 1) & 1u);
+    if (tid < RGN_ROWS * 2) {
+      const uint32_t* seg = Rc + tid * RI_WORDS;
+      uint32_t run = seg[6];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const uint32_t ec = tab[c];
-          slot_position<CO>(vp, a, ef0 + lf + ((ec >> 12) & 1u), em0 + lm + ((ec >> 13) & 1u),
-                            es0 + ls + ((ec >> 14) & 1u), ((ec >> 9) & 7u) >> 1, p[c][0], p[c][1], p[c][2]);
-        }
-        float* dst = a.normals + 3ull * (rv[warp][src] + vi - (SLAB ? rvo[warp][src] : 0u));
-        // legacy faces (t0,t2,t1) = the stored row reversed: corner k becomes corner 2-k
-        if (a.transpose) face_normal_corner(p[2], p[1], p[0], 2 - (int)k, dst);
-        else face_normal_corner(p[0], p[1], p[2], (int)k, dst);
+      for (int s = 0; s < 6; ++s) {
+        rb[tid * RI_WORDS + s] = run;
+        run += __popc(seg[s]);
       }
     }
-    __syncwarp();
-  }
-}
+    __syncthreads();
 
-// vertices: one CTA per non-empty tile, one thread per vertex slot of the tile (perm/vinfo are
-// read coalesced).  Final form (reference: _normalize_mesh zmesh/_zmesh.pyx:423-433): three
-// separately rounded float32 operations, no FMA.
-constexpr int NT_V = 128;
-template <bool CO>
-__global__ void __launch_bounds__(NT_V) k_vertices(const VolParams vp, const Pass2Args a) {
-  const TileHdr h = load_hdr(a.hdr + blockIdx.x);
-  if (h.nslots == 0) return;
-  uint32_t b = h.tile;
-  const uint32_t tf = b % vp.ntf;
-  b /= vp.ntf;
-  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
-  const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
-  const TLEntry* tl = a.tl + h.tlbase;
-  for (uint32_t i = threadIdx.x; i < h.nslots; i += NT_V) {
-    const uint32_t rank = __ldg(a.perm + h.gbase + i);
-    const uint32_t w = __ldg(a.vinfo + h.gbase + i);
-    const uint32_t vidx = w & 0x7FFu, s6 = (w >> 11) & 7u, ci = w >> 14;
-    const u64 dst = (tl[ci].a & 0xFFFFFFFFull) + rank;
+    // ---- faces ----
+    if (a.write_faces || NORMALS) {
+      const uint32_t nrec = h.nrec;
+      for (uint32_t base = warp * 32; base < nrec; base += NT) {
+        const uint32_t r = base + lane;
+        const bool valid = r < nrec;
+        const u64 w64 = valid ? __ldg(a.rec + h.recbase + r) : 0ull;
+        const uint32_t w = (uint32_t)w64;
+        const uint32_t vidx = w & 0x7FFu, cs = (w >> 11) & 0xFFu, ci = w >> 19;
+        const uint32_t nt = valid ? s_tricount[cs] : 0u;
+        uint32_t ntot;
+        const uint32_t tpre = warp_prefix3(nt, ltm, ntot);
+        if (valid) {
+          TLEntry e;
+          if (ci < (uint32_t)TLC) e = tls[ci];
+          else e = a.tl[h.tlbase + ci];
+          const uint32_t lf = vidx & 31u, lm = (vidx >> 5) & 7u, ls = vidx >> 8;
+          ru[warp][lane] = (ls * RM + lm) | (lf << 8) | (cs << 16);
+          rf[warp][lane] = e.b + (uint32_t)(w64 >> 32);
+          if (SLAB) rvo[warp][lane] = (uint32_t)(e.a >> 32);
+          if (NORMALS) rv[warp][lane] = e.a & 0xFFFFFFFFull;
+          for (uint32_t t = 0; t < nt; ++t) tlist[warp][tpre + t] = (uint8_t)((lane << 3) | t);
+        }
+        __syncwarp();
+        for (uint32_t q = lane; q < ntot; q += 32) {
+          const uint32_t tr = tlist[warp][q];
+          const uint32_t src = tr >> 3, t = tr & 7u;
+          const uint32_t uc = ru[warp][src];
+          const uint32_t r0 = uc & 0xFFu, lf0 = (uc >> 8) & 0xFFu;
+          const uint32_t tab = s_tab[(uc >> 16) * CASE_TRIS + t];
+          const uint32_t voff = SLAB ? rvo[warp][src] : 0u;
+          uint32_t vi[3];
+          float p[3][3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const uint32_t en = (tab >> (8 * k)) & 0xFFu;
+            const uint32_t rr = r0 + (en & 15u), lfx = lf0 + ((en >> 4) & 1u), slot = en >> 5;
+            // slot = 2*axis + side; side 0: the owner (lower) voxel carries the label, 1: the upper one
+            if (SLAB && rr - ftop9 < (uint32_t)RM) {
+              vi[k] = __ldg(a.foreign + 4ull * ((size_t)(em0 + rr - ftop9) * vp.Efp + ef0 + lfx) + slot);
+            } else {
+              const uint32_t idx = rr * RGN_WORDS + ((lfx >> 5) << 3) + slot;
+              const uint32_t g = rb[idx] + __popc(Rc[idx] & ((1u << (lfx & 31u)) - 1u));
+              vi[k] = __ldg(a.perm + g) + voff;
+            }
+            if (NORMALS) {
+              const uint32_t rs_ = (rr * 57u) >> 9;  // rr / 9 for rr < 90
+              slot_position<CO>(vp, a, ef0 + lfx, em0 + rr - rs_ * RM, es0 + rs_, slot >> 1, p[k][0], p[k][1], p[k][2]);
+            }
+          }
+          if (a.write_faces) {
+            uint32_t* f = a.faces + 3ull * (rf[warp][src] + t);
+            f[0] = vi[0]; f[1] = vi[1]; f[2] = vi[2];
+          }
+          if (NORMALS) {
+            float* nb = a.normals + 3ull * rv[warp][src];
+            float* d0 = nb + 3ull * (vi[0] - voff);
+            float* d1 = nb + 3ull * (vi[1] - voff);
+            float* d2 = nb + 3ull * (vi[2] - voff);
+            // legacy faces (t0,t2,t1) = the stored row reversed
+            if (a.transpose) face_normal_scatter(p[2], p[1], p[0], d2, d1, d0);
+            else face_normal_scatter(p[0], p[1], p[2], d0, d1, d2);
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- vertices ----
     if (a.write_verts) {
-      float p0, p1, p2;
-      slot_position<CO>(vp, a, ef0 + (vidx & 31u), em0 + ((vidx >> 5) & 7u), es0 + (vidx >> 8), s6 >> 1, p0, p1, p2);
-      if (a.voxel_centered) { p0 = __fadd_rn(p0, a.c0); p1 = __fadd_rn(p1, a.c1); p2 = __fadd_rn(p2, a.c2); }
-      float* v = a.verts + 3ull * dst;
-      v[0] = __fmul_rn(p0, 0.5f);  // == p / 2.0f exactly
-      v[1] = __fmul_rn(p1, 0.5f);
-      v[2] = __fmul_rn(p2, 0.5f);
+      for (uint32_t s = tid; s < h.nslots; s += NT) {
+        const uint32_t rank = __ldg(a.perm + h.gbase + s);
+        const uint32_t w = __ldg(a.vinfo + h.gbase + s);
+        const uint32_t vidx = w & 0x7FFu, s6 = (w >> 11) & 7u, ci = w >> 14;
+        const u64 ea = ci < (uint32_t)TLC ? tls[ci].a : a.tl[h.tlbase + ci].a;
+        const u64 dst = (ea & 0xFFFFFFFFull) + rank;
+        float p0, p1, p2;
+        slot_position<CO>(vp, a, ef0 + (vidx & 31u), em0 + ((vidx >> 5) & 7u), es0 + (vidx >> 8), s6 >> 1, p0, p1, p2);
+        if (a.voxel_centered) { p0 = __fadd_rn(p0, a.c0); p1 = __fadd_rn(p1, a.c1); p2 = __fadd_rn(p2, a.c2); }
+        float* v = a.verts + 3ull * dst;
+        v[0] = __fmul_rn(p0, 0.5f);  // == p / 2.0f exactly
+        v[1] = __fmul_rn(p1, 0.5f);
+        v[2] = __fmul_rn(p2, 0.5f);
+      }
     }
-    if (a.normalize) {
-      float* nn = a.normals + 3ull * dst;
-      float x = nn[0], y = nn[1], z = nn[2];
-      const float l = len3(x, y, z);
-      if (l != 1.0f) { x = __fdiv_rn(x, l); y = __fdiv_rn(y, l); z = __fdiv_rn(z, l); }  // 0/0 -> NaN like hat()
-      nn[0] = x; nn[1] = y; nn[2] = z;
-    }
+    __syncthreads();  // region buffer, slot bases, tl cache and header slot are free again
   }
 }
 
 // slab sharding: final (cross-shard) indices of the in-plane slots of this shard's FIRST plane, for
 // the shard below whose cubes reference them: dst[(em * Efp + ef) * 4 + slot] = label offset + rank
+constexpr int NT_V = 128;
 template <bool CO>
 __global__ void __launch_bounds__(NT_V) k_export_plane(const VolParams vp, const Pass2Args a, uint32_t* dst) {
   const TileHdr h = load_hdr(a.hdr + blockIdx.x);
