@@ -122,7 +122,6 @@ struct KernelSet {
   classify_fn classify[2];  // MODE 0 / MODE 1
   size_t smem[2];
   int row_pad;              // staged row length (elements) = TMA box extent along f
-  int grid0 = 0;            // persistent grid of the MODE 0 launch (filled by run_mesh)
 };
 
 template <typename L, bool CO>
@@ -316,12 +315,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   }
   ZM_CUDA(h, cudaEventRecord(h->ev[1], st));
 
-  KernelSet ks = kernel_set(label_bytes, c_order != 0);
-  {
-    int per_sm = 0;
-    ZM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)ks.classify[0], NT, ks.smem[0]));
-    ks.grid0 = h->num_sms * std::max(per_sm, 1);
-  }
+  const KernelSet ks = kernel_set(label_bytes, c_order != 0);
   CUtensorMap tmap;
   vp.use_tma = make_tensor_map(&tmap, vp.data, label_bytes, vp.nf, vp.nm, vp.ns, ks.row_pad) ? 1u : 0u;
 
@@ -360,7 +354,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
     Pass1Args p1{ht, d_ctl, h->d_rowinfo.as<uint32_t>(), h->d_perm.as<uint32_t>(),
                  h->d_vinfo.as<uint32_t>(), h->d_rec.as<u64>(), h->d_tl.as<TLEntry>(), h->d_hdr.as<TileHdr>(),
                  h->d_dense.as<uint32_t>(), capV, capR, capL};
-    ks.classify[0]<<<(uint32_t)std::min<unsigned long long>(ntiles, (unsigned long long)ks.grid0), NT, ks.smem[0], st>>>(vp, tmap, p1);
+    ks.classify[0]<<<(uint32_t)ntiles, NT, ks.smem[0], st>>>(vp, tmap, p1);
     ZM_CUDA(h, cudaGetLastError());
     const uint32_t dense_grid = (uint32_t)std::min<unsigned long long>(ntiles, 148ull);
     ks.classify[1]<<<dense_grid, NT, ks.smem[1], st>>>(vp, tmap, p1);

@@ -73,7 +73,7 @@ enum : uint32_t {
 // tiles that overflow it are queued and redone by the MODE 1 launch, which processes a tile as two
 // half tiles (4 s-planes each) whose capacities are the hard maxima (so it cannot overflow).
 template <int MODE> struct Caps;
-template <> struct Caps<0> { static constexpr int LT = 256, VCAP = 2048, RCAP = 2048, PROBES = 16, HALVES = 1; };
+template <> struct Caps<0> { static constexpr int LT = 128, VCAP = 2048, RCAP = 2048, PROBES = 16, HALVES = 1; };
 template <> struct Caps<1> { static constexpr int LT = 2048, VCAP = 6 * TILE_VOX / 2, RCAP = 8 * TILE_VOX / 2, PROBES = 2048, HALVES = 2; };
 
 struct VolParams {
@@ -186,6 +186,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tmap, 
       ::"r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -272,25 +276,37 @@ __device__ __forceinline__ uint32_t group_prefix3(uint32_t c, uint32_t grp, uint
 template <typename L, int MODE>
 struct __align__(128) P1Smem {
   static constexpr int RFP = RowPad<L>::value;
-  L lab[RS * RM * RFP];            // TMA destination: must stay first (128-byte aligned)
-  uint32_t pl[NROWS][RI_WORDS];    // per row segment: slot bit planes 0..5; [6] = slots of the row, then (S2) first slot of the row in the tile
-  uint32_t alist[TILE_VOX];        // active voxels: voxel-in-tile | slot mask << 11
+  union {
+    L lab[RS * RM * RFP];            // TMA destination: must stay first (128-byte aligned); live until S3 ends
+    struct {                         // live from S5 on
+      u64 tla[Caps<MODE>::LT];       // tl entry (word a) of the label
+      uint32_t lvb[Caps<MODE>::LT];  // first rank of the tile's vertices inside the label
+      uint16_t cidx[Caps<MODE>::LT]; // tile-local (compact) label index
+    };
+  };
+  uint32_t pl[NROWS][RI_WORDS];    // per row segment: slot bit planes 0..5; [6] slots of the row, then (S2) first slot of the row in the tile; [7] active-cube mask
   u64 lkeys[Caps<MODE>::LT];
   u64 mbar;
   u64 recbase;
   uint32_t lcnt[Caps<MODE>::LT];   // low 16: vertices of the label in this tile, high 16: triangles
-  uint32_t lvb[Caps<MODE>::LT];    // first rank of the tile's vertices inside the label
-  uint32_t vstage[Caps<MODE>::VCAP];  // per tile-local slot: local rank << 12 | table slot
+  // per tile-local slot.  MODE 0: local rank (11 bits) | table slot << 11 (7 bits) | voxel-in-tile << 18 | slot << 29;
+  // MODE 1: local rank << 12 | table slot, voxel-in-tile | slot << 11 in pstage
+  uint32_t vstage[Caps<MODE>::VCAP];
   uint32_t rstage[Caps<MODE>::RCAP];  // voxel-in-tile | case << 11 | table slot << 19
-  uint32_t tc[2][4];               // tile coordinates (tf, tm, ts) published by the thread that issues the TMA load
-  uint32_t nact, nrec, nlab, nslots, overflow, ok, gbase, tlbase, ci, ttot;
-  uint16_t pp[NROWS][8];           // tile-local index of the first slot of (row, plane)
-  uint16_t cidx[Caps<MODE>::LT];   // tile-local (compact) label index
-  uint16_t pstage[Caps<MODE>::VCAP];  // per tile-local slot: voxel-in-tile | slot << 11
+  uint32_t tc[4];                  // tile coordinates (tf, tm, ts)
+  uint32_t wtot[NW];               // per s-plane: slots | active voxels << 16
+  uint32_t nrec, overflow, ok1, ok2, gbase, tlbase, ci, ttot;
+  uint16_t alist[TILE_VOX];        // active voxels (voxel-in-tile), compacted
+  uint16_t actpre[NROWS];          // active voxels in earlier rows
+  uint16_t pstage[MODE == 0 ? 2 : Caps<MODE>::VCAP];
   uint16_t rtoff[Caps<MODE>::RCAP];   // per record: first face row inside the (tile,label) block
-  uint8_t tricount[256];
+  uint8_t m8[TILE_VOX];            // slot mask of every voxel of a row with active voxels
+  alignas(8) uint8_t pp8[NROWS][8];  // slots of the row in lower planes
 };
 static_assert(sizeof(P1Smem<u64, 1>) <= 227 * 1024 && sizeof(P1Smem<uint8_t, 1>) <= 227 * 1024, "dense mode must fit one SM");
+static_assert(sizeof(P1Smem<uint32_t, 0>) <= 44 * 1024 + 400, "MODE 0 / 4-byte labels: five CTAs per SM");
+static_assert(Caps<0>::VCAP <= 2048 && Caps<0>::LT <= 128, "MODE 0 vstage packing");
+static_assert(sizeof(P1Smem<u64, 0>) <= 55 * 1024, "MODE 0 / 8-byte labels: four CTAs per SM");
 
 extern __shared__ __align__(128) unsigned char zm_dyn_smem[];
 
@@ -305,23 +321,21 @@ __device__ __forceinline__ void stage_origin(const VolParams& vp, uint32_t tf, u
   c2 = (int)(ts * TS) + vp.s_shift;
 }
 
-// thread 0: publish the coordinates of `tile` in tc[slot] and (TMA path) start the load of its region
+// thread 0: publish the coordinates of `tile` and (TMA path) start the load of its region
 template <typename L, int MODE>
-__device__ __forceinline__ void publish_tile(const VolParams& vp, P1Smem<L, MODE>& S, uint32_t tile, int slot) {
+__device__ __forceinline__ void begin_tile(const VolParams& vp, const CUtensorMap* tmap, P1Smem<L, MODE>& S, uint32_t tile) {
   uint32_t b = tile;
   const uint32_t tf = b % vp.ntf;
   b /= vp.ntf;
-  S.tc[slot][0] = tf;
-  S.tc[slot][1] = b % vp.ntm;
-  S.tc[slot][2] = b / vp.ntm;
-}
-template <typename L, int MODE>
-__device__ __forceinline__ void issue_tile(const VolParams& vp, const CUtensorMap* tmap, P1Smem<L, MODE>& S, int slot) {
-  int c0, c1, c2;
-  stage_origin<L>(vp, S.tc[slot][0], S.tc[slot][1], S.tc[slot][2], c0, c1, c2);
-  fence_proxy_async();
-  mbar_expect_tx(&S.mbar, (uint32_t)(sizeof(L) * RS * RM * P1Smem<L, MODE>::RFP));
-  tma_load_3d(S.lab, tmap, &S.mbar, c0, c1, c2);
+  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
+  S.tc[0] = tf; S.tc[1] = tm; S.tc[2] = ts;
+  if (vp.use_tma) {
+    int c0, c1, c2;
+    stage_origin<L>(vp, tf, tm, ts, c0, c1, c2);
+    fence_proxy_async();
+    mbar_expect_tx(&S.mbar, (uint32_t)(sizeof(L) * RS * RM * P1Smem<L, MODE>::RFP));
+    tma_load_3d(S.lab, tmap, &S.mbar, c0, c1, c2);
+  }
 }
 
 // volumes TMA cannot address (row pitch or base not 16-byte aligned): the same box with plain loads
@@ -359,7 +373,6 @@ __device__ __forceinline__ bool region_uniform(const P1Smem<L, MODE>& S) {
     ref = make_uint4(r, r, r, r);
   }
   uint32_t acc = 0;
-#pragma unroll
   for (int i = threadIdx.x; i < NQ; i += NT) {
     const uint4 v = q[i];
     acc |= (v.x ^ ref.x) | (v.y ^ ref.y) | (v.z ^ ref.z) | (v.w ^ ref.w);
@@ -367,11 +380,12 @@ __device__ __forceinline__ bool region_uniform(const P1Smem<L, MODE>& S) {
   return __syncthreads_and(acc == 0u) != 0;
 }
 
-// all-zero rowinfo for the row segments of a tile without slots
-__device__ __forceinline__ void zero_rows(const VolParams& vp, const Pass1Args& o, uint32_t tf, uint32_t tm, uint32_t ts) {
+// all-zero rowinfo for the row segments of planes [h0, h0 + nh) of a tile without slots
+__device__ __forceinline__ void zero_rows(const VolParams& vp, const Pass1Args& o, uint32_t tf, uint32_t tm, uint32_t ts,
+                                          int h0, int nh) {
   const int tid = threadIdx.x;
-  if (tid < 2 * NROWS) {
-    const int row = tid >> 1;
+  const int row = tid >> 1;
+  if (tid < 2 * NROWS && row >= h0 * TM && row < (h0 + nh) * TM) {
     const uint32_t rs = ts * TS + row / TM, rm = tm * TM + row % TM;
     if (rs < vp.Es_own && rm < vp.Em)
       reinterpret_cast<uint4*>(o.rowinfo + (((size_t)rs * vp.Em + rm) * vp.ntf + tf) * RI_WORDS)[tid & 1] = make_uint4(0u, 0u, 0u, 0u);
@@ -381,6 +395,7 @@ __device__ __forceinline__ void zero_rows(const VolParams& vp, const Pass1Args& 
 // S1 of a tile.  Thread (lane = f, warp = s) marches over m keeping the four labels of the
 // previous row in registers: per step 4 shared loads and 4 label compares give the cube's
 // uniformity and the voxel's slot mask; six ballots turn the masks of a row into its bit planes.
+// No atomics and no cross-step dependencies besides the marching registers.
 // INTERIOR tiles (no volume boundary within reach) skip all validity logic.
 template <typename L, int MODE, bool INTERIOR>
 __device__ __forceinline__ bool scan_tile(const VolParams& vp, P1Smem<L, MODE>& S, const L* lab,
@@ -388,7 +403,6 @@ __device__ __forceinline__ bool scan_tile(const VolParams& vp, P1Smem<L, MODE>& 
   constexpr int RFP = P1Smem<L, MODE>::RFP;
   constexpr uint32_t FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, ls = threadIdx.x >> 5;
-  const uint32_t ltm = (1u << lane) - 1u;
   const uint32_t ef = ef0 + lane, es = es0 + ls;
   const bool okf = INTERIOR || ef < vp.Ef, oks = INTERIOR || es < vp.Es_own;
   const bool nf1 = INTERIOR || ef + 1 < vp.Ef, ns1 = INTERIOR || es + 1 < vp.Es;
@@ -422,28 +436,26 @@ __device__ __forceinline__ bool scan_tile(const VolParams& vp, P1Smem<L, MODE>& 
       act = (m != 0u) || (valid && nf1 && nm1 && ns1 && !uniform);
     }
     const uint32_t ab = __ballot_sync(FULL, act);
-    if (ab) {  // (m != 0 implies act, so rows without active voxels keep their cleared planes)
+    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+    if (ab) {  // (m != 0 implies act)
       any = true;
       if (INTERIOR) {
         if (nef) m |= (za ? 1u : 0u) | (zf ? 2u : 0u);
         if (nem) m |= (za ? 4u : 0u) | (zm ? 8u : 0u);
         if (nes) m |= (za ? 16u : 0u) | (zs ? 32u : 0u);
       }
+      S.m8[(ls * TM + j) * TF + lane] = (uint8_t)m;
       if (__ballot_sync(FULL, m != 0u)) {
-        const uint32_t b0 = __ballot_sync(FULL, m & 1u), b1 = __ballot_sync(FULL, m & 2u);
-        const uint32_t b2 = __ballot_sync(FULL, m & 4u), b3 = __ballot_sync(FULL, m & 8u);
-        const uint32_t b4 = __ballot_sync(FULL, m & 16u), b5 = __ballot_sync(FULL, m & 32u);
-        if (lane == 0) {
-          uint32_t* row = S.pl[ls * TM + j];
-          *reinterpret_cast<uint4*>(row) = make_uint4(b0, b1, b2, b3);
-          *reinterpret_cast<uint4*>(row + 4) =
-              make_uint4(b4, b5, __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3) + __popc(b4) + __popc(b5), 0u);
-        }
+        b0 = __ballot_sync(FULL, m & 1u); b1 = __ballot_sync(FULL, m & 2u);
+        b2 = __ballot_sync(FULL, m & 4u); b3 = __ballot_sync(FULL, m & 8u);
+        b4 = __ballot_sync(FULL, m & 16u); b5 = __ballot_sync(FULL, m & 32u);
       }
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&S.nact, (uint32_t)__popc(ab));
-      base = __shfl_sync(FULL, base, 0);
-      if (act) S.alist[base + __popc(ab & ltm)] = (uint32_t)((ls * TM + j) * TF + lane) | (m << 11);
+    }
+    if (lane == 0) {
+      uint32_t* row = S.pl[ls * TM + j];
+      *reinterpret_cast<uint4*>(row) = make_uint4(b0, b1, b2, b3);
+      *reinterpret_cast<uint4*>(row + 4) =
+          make_uint4(b4, b5, __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3) + __popc(b4) + __popc(b5), ab);
     }
     a = am; af = amf; as_ = ams;
     nef = nef2; nes = nes2; eq_row = eq_row2;
@@ -452,24 +464,13 @@ __device__ __forceinline__ bool scan_tile(const VolParams& vp, P1Smem<L, MODE>& 
   return any;
 }
 
-// clear the per-tile tables (all threads; caller synchronises)
-template <typename L, int MODE>
-__device__ __forceinline__ void clear_tables(P1Smem<L, MODE>& S) {
-  constexpr int LT = Caps<MODE>::LT;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
-  uint4* plq = reinterpret_cast<uint4*>(&S.pl[0][0]);
-  for (int i = tid; i < NROWS * RI_WORDS / 4; i += NT) plq[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (tid == 0) { S.nact = 0; S.nrec = 0; S.nlab = 0; S.overflow = 0; S.ci = 0; S.ttot = 0; }
-}
+enum : int { TILE_EMPTY = 0, TILE_DEFERRED = 1, TILE_DONE = 2 };
 
-enum : int { TILE_EMPTY = 0, TILE_DEFERRED = 1, TILE_ACTIVE = 2 };
-
-// S1-S3 of a (half) tile: everything that reads the staged labels.  Ends with a barrier after
-// which the region is dead.  Planes [h0, h0 + nh) of the tile are processed (all 8 in MODE 0).
+// Everything after staging for planes [h0, h0 + nh) of a tile (all 8 in MODE 0).  The caller has
+// staged the region and synchronised; the per-tile tables are cleared here.
 template <typename L, bool CO, int MODE>
-__device__ __forceinline__ int tile_front(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const uint32_t tile,
-                                          const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh) {
+__device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const uint32_t tile,
+                                         const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh) {
   constexpr int RFP = P1Smem<L, MODE>::RFP;
   constexpr int LT = Caps<MODE>::LT, VCAP = Caps<MODE>::VCAP, RCAP = Caps<MODE>::RCAP, PROBES = Caps<MODE>::PROBES;
   constexpr uint32_t FULL = 0xffffffffu;
@@ -479,61 +480,89 @@ __device__ __forceinline__ int tile_front(const VolParams& vp, const Pass1Args& 
   const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
   const L* const lab = S.lab + (vp.pad ? ALIGN - 1 : 0);
 
-  // ---- S1: slot masks -> bit planes, compaction of active voxels ----
+  for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
+  if (tid == 0) { S.nrec = 0; S.overflow = 0; S.ci = 0; S.ttot = 0; }
+
+  // ---- S1: slot masks -> bit planes, active-cube masks ----
   bool any = false;
   if (warp >= h0 && warp < h0 + nh) {
     if (ef0 + TF + 1 <= vp.Ef && em0 + TM + 1 <= vp.Em && es0 + TS + 1 <= vp.Es)
       any = scan_tile<L, MODE, true>(vp, S, lab, ef0, em0, es0);
     else
       any = scan_tile<L, MODE, false>(vp, S, lab, ef0, em0, es0);
+  } else if (lane < TM) {
+    uint4* row = reinterpret_cast<uint4*>(S.pl[warp * TM + lane]);
+    row[0] = make_uint4(0u, 0u, 0u, 0u);
+    row[1] = make_uint4(0u, 0u, 0u, 0u);
   }
+  __syncwarp();
+  // ---- S2 (per warp, no serial section): in-row plane prefixes, row prefixes inside the plane ----
+  uint32_t packed = 0;  // slots of the row | active voxels of the row << 16   (lane j < TM: row j of the plane)
+  if (lane < TM) {
+    const int row = warp * TM + lane;
+    const uint4 q0 = *reinterpret_cast<const uint4*>(&S.pl[row][0]);
+    const uint4 q1 = *reinterpret_cast<const uint4*>(&S.pl[row][4]);
+    const uint32_t c0 = __popc(q0.x), c1 = c0 + __popc(q0.y), c2 = c1 + __popc(q0.z), c3 = c2 + __popc(q0.w);
+    const uint32_t c4 = c3 + __popc(q1.x);
+    *reinterpret_cast<uint2*>(S.pp8[row]) = make_uint2((c0 << 8) | (c1 << 16) | (c2 << 24), c3 | (c4 << 8));
+    packed = q1.z | ((uint32_t)__popc(q1.w) << 16);
+  }
+  uint32_t rinc = packed;
+#pragma unroll
+  for (int d = 1; d < TM; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL, rinc, d);
+    if (lane >= d) rinc += t;
+  }
+  if (lane == TM - 1) S.wtot[warp] = rinc;
   if (!__syncthreads_or(any ? 1 : 0)) return TILE_EMPTY;
-
-  // ---- S2: first slot of every row and of every (row, plane) inside the tile ----
-  if (warp == 0) {
-    const uint32_t a0 = S.pl[2 * lane][6], a1 = S.pl[2 * lane + 1][6];
-    const uint32_t sum = a0 + a1;
-    uint32_t inc = sum;
+  uint32_t nslots, nact;
+  {
+    const uint32_t t = S.wtot[lane & (NW - 1)];
+    uint32_t winc = t;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t t = __shfl_up_sync(FULL, inc, d);
-      if (lane >= d) inc += t;
+    for (int d = 1; d < NW; d <<= 1) {
+      const uint32_t x = __shfl_up_sync(FULL, winc, d, NW);
+      if ((lane & (NW - 1)) >= d) winc += x;
     }
-    if (lane == 31) S.nslots = inc;
-    uint32_t run = inc - sum;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      uint32_t* row = S.pl[2 * lane + r];
-      row[6] = run;
-#pragma unroll
-      for (int s = 0; s < 6; ++s) {
-        S.pp[2 * lane + r][s] = (uint16_t)run;
-        run += __popc(row[s]);
-      }
+    const uint32_t wbase = __shfl_sync(FULL, winc - t, warp);
+    const uint32_t total = __shfl_sync(FULL, winc, NW - 1);
+    nslots = total & 0xFFFFu;
+    nact = total >> 16;
+    if (lane < TM) {
+      const uint32_t ex = wbase + rinc - packed;
+      S.pl[warp * TM + lane][6] = ex & 0xFFFFu;
+      S.actpre[warp * TM + lane] = (uint16_t)(ex >> 16);
     }
   }
-  __syncthreads();
-  const uint32_t nslots = S.nslots, nact = S.nact;
   if (MODE == 0 && nslots > (uint32_t)VCAP) {
     if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
     return TILE_DEFERRED;
   }
+  __syncwarp();
+  // compaction of the active voxels of the warp's own plane
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    const int row = warp * TM + j;
+    const uint32_t mask = S.pl[row][7];
+    if ((mask >> lane) & 1u) S.alist[S.actpre[row] + __popc(mask & ltm)] = (uint16_t)(row * TF + lane);
+  }
+  __syncthreads();
 
   // ---- S3: per active voxel: distinct labels of its cube -> counts, local ranks, records ----
   for (uint32_t base = warp * 32; base < nact; base += NT) {
     const uint32_t i = base + lane;
     const bool valid = i < nact;
-    const uint32_t aw = valid ? S.alist[i] : 0u;
-    const uint32_t vidx = aw & 0x7FFu;
+    const uint32_t vidx = valid ? S.alist[i] : 0u;
     const int lf = vidx & 31, lm = (vidx >> 5) & 7, ls = vidx >> 8;
     L c[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
       c[n] = lab[((ls + corner_ds<CO>(n)) * RM + (lm + corner_dm<CO>(n))) * RFP + (lf + corner_df<CO>(n))];
-    const uint32_t m = (aw >> 11) & 63u;
+    const uint32_t m = S.m8[vidx];
     const bool cube = (ef0 + lf + 1 < vp.Ef) && (em0 + lm + 1 < vp.Em) && (es0 + ls + 1 < vp.Es);
     const uint32_t row = vidx >> 5;
     const uint32_t ltf = (1u << lf) - 1u;
+    const uint32_t rowpre = S.pl[row][6];
     uint32_t acc = valid ? 0u : 0xFFu;
     while (__any_sync(FULL, acc != 0xFFu)) {
       const bool have = acc != 0xFFu;
@@ -548,7 +577,7 @@ __device__ __forceinline__ int tile_front(const VolParams& vp, const Pass1Args& 
       const uint32_t cs = ~msk & 0xFFu;
       uint32_t nt = 0, mine = 0;
       if (have && label != 0) {
-        if (cube) nt = S.tricount[cs];
+        if (cube) nt = __ldg(&TRI_COUNT_D[cs]);
         mine = (((msk >> 0) & 1u) * 0x15u) | (((msk >> corner_plus_f<CO>()) & 1u) << 1) |
                (((msk >> corner_plus_m<CO>()) & 1u) << 3) | (((msk >> corner_plus_s<CO>()) & 1u) << 5);
         mine &= m;
@@ -577,9 +606,13 @@ __device__ __forceinline__ int tile_front(const VolParams& vp, const Pass1Args& 
         while (mm) {
           const int s6 = __ffs(mm) - 1;
           mm &= mm - 1u;
-          const uint32_t lg = (uint32_t)S.pp[row][s6] + __popc(S.pl[row][s6] & ltf);
-          S.vstage[lg] = (r << 12) | (uint32_t)hs;
-          S.pstage[lg] = (uint16_t)(vidx | ((uint32_t)s6 << 11));
+          const uint32_t lg = rowpre + S.pp8[row][s6] + __popc(S.pl[row][s6] & ltf);
+          if (MODE == 0) {
+            S.vstage[lg] = r | ((uint32_t)hs << 11) | (vidx << 18) | ((uint32_t)s6 << 29);
+          } else {
+            S.vstage[lg] = (r << 12) | (uint32_t)hs;
+            S.pstage[lg] = (uint16_t)(vidx | ((uint32_t)s6 << 11));
+          }
           ++r;
         }
       }
@@ -601,7 +634,7 @@ __device__ __forceinline__ int tile_front(const VolParams& vp, const Pass1Args& 
       }
     }
   }
-  __syncthreads();
+  __syncthreads();  // the staged labels are dead from here on (lvb / cidx reuse their memory)
   if (S.overflow) {
     if (MODE == 0) {
       if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
@@ -610,56 +643,18 @@ __device__ __forceinline__ int tile_front(const VolParams& vp, const Pass1Args& 
     }
     return TILE_DEFERRED;
   }
-  return TILE_ACTIVE;
-}
 
-// S5-S6 of a (half) tile: reservations and the coalesced flush.  Does not touch the staged labels.
-template <typename L, int MODE>
-__device__ __forceinline__ void tile_back(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const uint32_t tile,
-                                          const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh) {
-  constexpr int LT = Caps<MODE>::LT;
-  constexpr uint32_t FULL = 0xffffffffu;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t nslots = S.nslots;
-
-  // ---- S5: reserve the tile's segments and the per-label ranges ----
-  {
-    uint32_t nl = 0;
-    for (int i = tid; i < LT; i += NT) nl += (S.lkeys[i] != 0ull) ? 1u : 0u;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) nl += __shfl_xor_sync(FULL, nl, d);
-    if (lane == 0 && nl) atomicAdd(&S.nlab, nl);
-  }
-  __syncthreads();
+  // ---- S5: reservations.  Thread 0's global atomics overlap the per-label ones of the others ----
+  const uint32_t nrec = S.nrec;
   if (tid == 0) {
-    const uint32_t nrec = S.nrec, nlab = S.nlab;
     const u64 gbase = nslots ? atomicAdd(&o.ctl->cur_perm, (u64)nslots) : 0ull;
     const u64 recbase = nrec ? atomicAdd(&o.ctl->cur_rec, (u64)nrec) : 0ull;
-    const u64 tlbase = nlab ? atomicAdd(&o.ctl->cur_tl, (u64)nlab) : 0ull;
-    const bool ok = gbase + nslots <= o.capV && recbase + nrec <= o.capR && tlbase + nlab <= o.capL;
+    const bool ok = gbase + nslots <= o.capV && recbase + nrec <= o.capR;
     if (!ok) atomicOr(&o.ctl->flags, FLAG_CAP);
-    else {
-      TileHdr h;
-      h.recbase = recbase;
-      h.gbase = (uint32_t)gbase;
-      h.tlbase = (uint32_t)tlbase;
-      h.nslots = (uint16_t)nslots;
-      h.nrec = (uint16_t)nrec;
-      h.nlab = (uint16_t)nlab;
-      h.pad = 0;
-      h.tile = tile;
-      h.pad2 = 0;
-      o.hdr[atomicAdd(&o.ctl->work_count, 1u)] = h;
-    }
     S.gbase = (uint32_t)gbase;
     S.recbase = recbase;
-    S.tlbase = (uint32_t)tlbase;
-    S.ok = ok ? 1u : 0u;
+    S.ok1 = ok ? 1u : 0u;
   }
-  __syncthreads();
-  if (!S.ok) return;  // capacity guess too small: the cursors still give the exact need; host reruns
-  const uint32_t gbase = S.gbase, tlbase = S.tlbase;
-  const u64 recbase = S.recbase;
   for (int i = tid; i < LT; i += NT) {
     const u64 label = S.lkeys[i];
     if (label != 0ull) {
@@ -668,20 +663,40 @@ __device__ __forceinline__ void tile_back(const VolParams& vp, const Pass1Args& 
       const int gs = gtab_insert(o.ht, label, &o.ctl->flags);
       u64 old = 0;
       if (gs >= 0) old = atomicAdd(&o.ht.cnt[gs], (u64)nv | ((u64)nt << 32));
-      const uint32_t ci = atomicAdd(&S.ci, 1u);
       S.lvb[i] = (uint32_t)old;
-      S.cidx[i] = (uint16_t)ci;
-      TLEntry e;
-      e.a = (u64)(uint32_t)(gs >= 0 ? gs : 0) | (old & 0xFFFFFFFF00000000ull);
-      e.b = 0;
-      o.tl[tlbase + ci] = e;
+      S.cidx[i] = (uint16_t)atomicAdd(&S.ci, 1u);
+      S.tla[i] = (u64)(uint32_t)(gs >= 0 ? gs : 0) | (old & 0xFFFFFFFF00000000ull);
       if (nt) atomicAdd(&S.ttot, nt);
     }
   }
   __syncthreads();
+  if (!S.ok1) return TILE_DONE;  // capacity guess too small: the cursors still give the exact need; host reruns
+  const uint32_t gbase = S.gbase;
+  const u64 recbase = S.recbase;
+  if (tid == 0) {  // tl block + work-list entry; the latency of these atomics hides behind the flush below
+    const uint32_t nlab = S.ci;
+    const u64 tlbase = nlab ? atomicAdd(&o.ctl->cur_tl, (u64)nlab) : 0ull;
+    const bool ok = tlbase + nlab <= o.capL;
+    if (!ok) atomicOr(&o.ctl->flags, FLAG_CAP);
+    else {
+      TileHdr h;
+      h.recbase = recbase;
+      h.gbase = gbase;
+      h.tlbase = (uint32_t)tlbase;
+      h.nslots = (uint16_t)nslots;
+      h.nrec = (uint16_t)nrec;
+      h.nlab = (uint16_t)nlab;
+      h.pad = 0;
+      h.tile = tile;
+      h.pad2 = 0;
+      o.hdr[atomicAdd(&o.ctl->work_count, 1u)] = h;
+      if (S.ttot) atomicAdd(&o.ctl->cur_tri, (u64)S.ttot);
+    }
+    S.tlbase = (uint32_t)tlbase;
+    S.ok2 = ok ? 1u : 0u;
+  }
 
   // ---- S6: flush rowinfo, perm/vinfo and the records (coalesced) ----
-  if (tid == 0 && S.ttot) atomicAdd(&o.ctl->cur_tri, (u64)S.ttot);
   {
     const int row = tid >> 2, q = tid & 3;  // 4 threads per row segment, 8 bytes each
     if (row >= h0 * TM && row < (h0 + nh) * TM) {
@@ -695,104 +710,89 @@ __device__ __forceinline__ void tile_back(const VolParams& vp, const Pass1Args& 
   }
   for (uint32_t i = tid; i < nslots; i += NT) {
     const uint32_t w = S.vstage[i];
-    const uint32_t hs = w & 0xFFFu;
-    o.perm[(size_t)gbase + i] = S.lvb[hs] + (w >> 12);
-    o.vinfo[(size_t)gbase + i] = (uint32_t)S.pstage[i] | ((uint32_t)S.cidx[hs] << 14);
+    if (MODE == 0) {
+      const uint32_t hs = (w >> 11) & 0x7Fu;
+      o.perm[(size_t)gbase + i] = S.lvb[hs] + (w & 0x7FFu);
+      o.vinfo[(size_t)gbase + i] = (w >> 18) | ((uint32_t)S.cidx[hs] << 14);
+    } else {
+      const uint32_t hs = w & 0xFFFu;
+      o.perm[(size_t)gbase + i] = S.lvb[hs] + (w >> 12);
+      o.vinfo[(size_t)gbase + i] = (uint32_t)S.pstage[i] | ((uint32_t)S.cidx[hs] << 14);
+    }
   }
-  const uint32_t nrec = S.nrec;
   for (uint32_t i = tid; i < nrec; i += NT) {
     const uint32_t w = S.rstage[i];
     o.rec[recbase + i] = (u64)((w & 0x7FFFFu) | ((uint32_t)S.cidx[w >> 19] << 19)) | ((u64)S.rtoff[i] << 32);
   }
+  __syncthreads();
+  if (!S.ok2) return TILE_DONE;
+  const uint32_t tlbase = S.tlbase;
+  for (int i = tid; i < LT; i += NT) {
+    if (S.lkeys[i] != 0ull) {
+      TLEntry e;
+      e.a = S.tla[i];
+      e.b = 0;
+      o.tl[tlbase + S.cidx[i]] = e;
+    }
+  }
+  return TILE_DONE;
 }
 
-// MODE 0: persistent CTAs, tile t -> CTA t mod gridDim.  One label buffer per CTA: the load of the
-// next tile is issued the moment the current region is dead (after the uniform test of a uniform
-// tile, after S3 of an active one) and overlaps the flush.  MODE 1: the queued dense tiles.
+// MODE 0: one CTA per tile (the hardware CTA scheduler overlaps the TMA wait of one tile with the
+// work of the others resident on the SM).  MODE 1: the queued dense tiles, two half tiles each.
+constexpr uint32_t PREFETCH_DISTANCE = 148 * 6;  // tiles ahead (in launch order) whose region is pulled into L2
 template <typename L, bool CO, int MODE>
-__global__ void __launch_bounds__(NT, MODE == 0 ? 4 : 1) k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap,
-                                                 const Pass1Args o) {
+__global__ void __launch_bounds__(NT, MODE == 0 ? (sizeof(L) == 8 ? 4 : 5) : 1)
+k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const Pass1Args o) {
   P1Smem<L, MODE>& S = *reinterpret_cast<P1Smem<L, MODE>*>(zm_dyn_smem);
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&S.mbar, 1);
     fence_mbar_init();
   }
-  S.tricount[tid] = TRI_COUNT_D[tid];
-  clear_tables(S);
-  uint32_t parity = 0;
   if (MODE == 0) {
-    const uint32_t ntiles = vp.ntf * vp.ntm * vp.nts;
-    uint32_t tile = blockIdx.x;
-    if (tile >= ntiles) return;
+    const uint32_t tile = blockIdx.x;
     if (tid == 0) {
-      publish_tile(vp, S, tile, 0);
-      if (vp.use_tma) issue_tile(vp, &tmap, S, 0);
-    }
-    __syncthreads();
-    bool dirty = false;
-    for (uint32_t it = 0; tile < ntiles; ++it) {
-      const uint32_t next = tile + gridDim.x;
-      const int cur = it & 1;
-      const uint32_t tf = S.tc[cur][0], tm = S.tc[cur][1], ts = S.tc[cur][2];
-      if (tid == 0 && next < ntiles) publish_tile(vp, S, next, cur ^ 1);
-      if (vp.use_tma) {
-        mbar_wait(&S.mbar, parity);  // every thread waits itself: the TMA writes are visible to it afterwards
-        parity ^= 1u;
-      } else {
-        stage_plain(vp, S, tf, tm, ts);
-        __syncthreads();
+      begin_tile(vp, &tmap, S, tile);
+      uint32_t pt = tile + PREFETCH_DISTANCE;
+      if (vp.use_tma && pt < vp.ntf * vp.ntm * vp.nts) {
+        const uint32_t ptf = pt % vp.ntf;
+        pt /= vp.ntf;
+        int c0, c1, c2;
+        stage_origin<L>(vp, ptf, pt % vp.ntm, pt / vp.ntm, c0, c1, c2);
+        tma_prefetch_3d(&tmap, c0, c1, c2);
       }
-      int status = TILE_EMPTY;
-      if (!region_uniform(S)) {
-        if (dirty) {
-          clear_tables(S);
-          __syncthreads();
-          dirty = false;
-        }
-        status = tile_front<L, CO, MODE>(vp, o, S, tile, tf, tm, ts, 0, TS);
-        dirty = true;
-      }
-      // the staged region is dead (every path above ends with a barrier): fetch the next one
-      if (tid == 0 && vp.use_tma && next < ntiles) issue_tile(vp, &tmap, S, cur ^ 1);
-      if (status == TILE_EMPTY) zero_rows(vp, o, tf, tm, ts);
-      else if (status == TILE_ACTIVE) tile_back<L, MODE>(vp, o, S, tile, tf, tm, ts, 0, TS);
-      if (!vp.use_tma || status != TILE_EMPTY) __syncthreads();
-      tile = next;
     }
+    __syncthreads();  // mbarrier initialised, coordinates published
+    const uint32_t tf = S.tc[0], tm = S.tc[1], ts = S.tc[2];
+    if (vp.use_tma) {
+      mbar_wait(&S.mbar, 0);  // every thread waits itself: the TMA writes are visible to it afterwards
+    } else {
+      stage_plain(vp, S, tf, tm, ts);
+      __syncthreads();
+    }
+    int status = TILE_EMPTY;
+    if (!region_uniform(S)) status = tile_body<L, CO, MODE>(vp, o, S, tile, tf, tm, ts, 0, TS);
+    if (status == TILE_EMPTY) zero_rows(vp, o, tf, tm, ts, 0, TS);
   } else {
     const uint32_t n = o.ctl->dense_count;  // written by the MODE 0 launch that precedes this one
-    __syncthreads();
+    uint32_t parity = 0;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
       const uint32_t tile = o.dense_list[i];
-      if (tid == 0) {
-        publish_tile(vp, S, tile, 0);
-        if (vp.use_tma) issue_tile(vp, &tmap, S, 0);
-      }
-      __syncthreads();
-      const uint32_t tf = S.tc[0][0], tm = S.tc[0][1], ts = S.tc[0][2];
-      if (vp.use_tma) {
-        mbar_wait(&S.mbar, parity);
-        parity ^= 1u;
-      } else {
-        stage_plain(vp, S, tf, tm, ts);
-        __syncthreads();
-      }
       for (int half = 0; half < Caps<MODE>::HALVES; ++half) {
         const int nh = TS / Caps<MODE>::HALVES, h0 = half * nh;
-        if (i != blockIdx.x || half != 0) clear_tables(S);
+        if (tid == 0) begin_tile(vp, &tmap, S, tile);  // (the region is staged again: lvb / cidx of the first half overwrote it)
         __syncthreads();
-        const int status = tile_front<L, CO, MODE>(vp, o, S, tile, tf, tm, ts, h0, nh);
-        if (status == TILE_ACTIVE) tile_back<L, MODE>(vp, o, S, tile, tf, tm, ts, h0, nh);
-        else if (status == TILE_EMPTY) {
-          // rows of this half without slots
-          const int row = tid >> 1;
-          if (tid < 2 * NROWS && row >= h0 * TM && row < (h0 + nh) * TM) {
-            const uint32_t rs = ts * TS + row / TM, rm = tm * TM + row % TM;
-            if (rs < vp.Es_own && rm < vp.Em)
-              reinterpret_cast<uint4*>(o.rowinfo + (((size_t)rs * vp.Em + rm) * vp.ntf + tf) * RI_WORDS)[tid & 1] = make_uint4(0u, 0u, 0u, 0u);
-          }
+        const uint32_t tf = S.tc[0], tm = S.tc[1], ts = S.tc[2];
+        if (vp.use_tma) {
+          mbar_wait(&S.mbar, parity);
+          parity ^= 1u;
+        } else {
+          stage_plain(vp, S, tf, tm, ts);
+          __syncthreads();
         }
+        const int status = tile_body<L, CO, MODE>(vp, o, S, tile, tf, tm, ts, h0, nh);
+        if (status == TILE_EMPTY) zero_rows(vp, o, tf, tm, ts, h0, nh);
         __syncthreads();
       }
     }
@@ -1010,10 +1010,10 @@ __device__ __forceinline__ void slot_position(const VolParams& vp, const Pass2Ar
   else             { p0 = __fmul_rn(a.r0, kx); p1 = __fmul_rn(a.r1, ky); p2 = __fmul_rn(a.r2, kz); }
 }
 
-// per (case, triangle): three bytes, one per output corner, in the reference winding of Mesher.get:
-// (E[T[3n+1]], E[T[3n]], E[T[3n+2]])  (marching_cubes.hpp:338-343 then cMesher.hpp:158-162).
-// Byte: row delta of the owner voxel (ds * RM + dm, 4 bits) | its f offset << 4 | slot << 5.
-// Filled by prepare_device.
+// per (case, triangle): three 9-bit fields, one per output corner, in the reference winding of
+// Mesher.get: (E[T[3n+1]], E[T[3n]], E[T[3n+2]])  (marching_cubes.hpp:338-343 then cMesher.hpp:158-162).
+// Field: slot | row delta of the owner voxel (ds * RM + dm) << 4 | its f offset << 8, i.e. the low
+// 8 bits are the word offset of (row, plane) inside the staged region.  Filled by prepare_device.
 constexpr int CASE_TRIS = 5;
 __device__ __align__(16) uint32_t CASE_TAB_D[2][256 * CASE_TRIS];
 
@@ -1031,9 +1031,9 @@ inline void build_case_table(uint32_t* tab) {
         if (t < TRI_COUNT[cs] && ed < 12) {
           const uint32_t i = info[ed];
           const uint32_t slot = ((i >> 12) & 7u) + (((uint32_t)cs >> ((i >> 16) & 7u)) & 1u);
-          v = (i & 0x1Fu) | (slot << 5);
+          v = slot | ((i & 0xFu) << 4) | (((i >> 4) & 1u) << 8);
         }
-        w |= v << (8 * k);
+        w |= v << (9 * k);
       }
       tab[cs * CASE_TRIS + t] = w;
     }
@@ -1059,7 +1059,7 @@ constexpr int RGN_WORDS = 2 * RI_WORDS;      // two row segments per region row
 constexpr int RGN_PAD = 1312;                // words per staged region buffer (5184 B rounded up to 128 B)
 constexpr int TLC = 64;                      // tile-local labels whose tl entry is cached in shared memory
 template <bool CO, bool NORMALS, bool SLAB>
-__global__ void __launch_bounds__(NT, NORMALS ? 3 : 4) k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap,
+__global__ void __launch_bounds__(NT, NORMALS ? 3 : 5) k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap,
                                                              const Pass2Args a) {
   constexpr uint32_t FULL = 0xffffffffu;
   __shared__ __align__(128) uint32_t R[2][RGN_PAD];   // TMA destinations: rowinfo of the region
@@ -1071,7 +1071,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 4) k_emit(const VolParams vp
   __shared__ uint8_t s_tricount[256];
   __shared__ u64 rf[NW][32];              // per record of the warp's batch: first face row
   __shared__ u64 rv[NW][32];              //                                  first vertex row of the label
-  __shared__ uint32_t ru[NW][32];         //                                  region row | f << 8 | case << 16
+  __shared__ uint32_t ru[NW][32];         //                                  region row * 16 | f << 11 | case << 16
   __shared__ uint32_t rvo[NW][32];        //                                  index offset of the label (earlier shards)
   __shared__ uint8_t tlist[NW][160];      // triangles of the batch: record lane << 3 | t
 
@@ -1146,10 +1146,13 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 4) k_emit(const VolParams vp
     // ---- faces ----
     if (a.write_faces || NORMALS) {
       const uint32_t nrec = h.nrec;
-      for (uint32_t base = warp * 32; base < nrec; base += NT) {
-        const uint32_t r = base + lane;
-        const bool valid = r < nrec;
-        const u64 w64 = valid ? __ldg(a.rec + h.recbase + r) : 0ull;
+      const u64* recp = a.rec + h.recbase;
+      uint32_t base = warp * 32;
+      u64 wnext = base + lane < nrec ? __ldg(recp + base + lane) : 0ull;
+      for (; base < nrec; base += NT) {
+        const bool valid = base + lane < nrec;
+        const u64 w64 = wnext;
+        wnext = base + NT + lane < nrec ? __ldg(recp + base + NT + lane) : 0ull;  // next batch in flight during this one
         const uint32_t w = (uint32_t)w64;
         const uint32_t vidx = w & 0x7FFu, cs = (w >> 11) & 0xFFu, ci = w >> 19;
         const uint32_t nt = valid ? s_tricount[cs] : 0u;
@@ -1160,7 +1163,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 4) k_emit(const VolParams vp
           if (ci < (uint32_t)TLC) e = tls[ci];
           else e = a.tl[h.tlbase + ci];
           const uint32_t lf = vidx & 31u, lm = (vidx >> 5) & 7u, ls = vidx >> 8;
-          ru[warp][lane] = (ls * RM + lm) | (lf << 8) | (cs << 16);
+          ru[warp][lane] = ((ls * RM + lm) << 4) | (lf << 11) | (cs << 16);
           rf[warp][lane] = e.b + (uint32_t)(w64 >> 32);
           if (SLAB) rvo[warp][lane] = (uint32_t)(e.a >> 32);
           if (NORMALS) rv[warp][lane] = e.a & 0xFFFFFFFFull;
@@ -1171,20 +1174,22 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 4) k_emit(const VolParams vp
           const uint32_t tr = tlist[warp][q];
           const uint32_t src = tr >> 3, t = tr & 7u;
           const uint32_t uc = ru[warp][src];
-          const uint32_t r0 = uc & 0xFFu, lf0 = (uc >> 8) & 0xFFu;
+          const uint32_t u0 = uc & 0x7FFu, lf0 = (uc >> 11) & 31u;
           const uint32_t tab = s_tab[(uc >> 16) * CASE_TRIS + t];
           const uint32_t voff = SLAB ? rvo[warp][src] : 0u;
           uint32_t vi[3];
           float p[3][3];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const uint32_t en = (tab >> (8 * k)) & 0xFFu;
-            const uint32_t rr = r0 + (en & 15u), lfx = lf0 + ((en >> 4) & 1u), slot = en >> 5;
+            const uint32_t en = (tab >> (9 * k)) & 0x1FFu;
+            const uint32_t lfx = lf0 + (en >> 8), slot = en & 7u;
+            const uint32_t uw = u0 + (en & 0xFFu);  // word of (row, plane) in the first segment
+            const uint32_t rr = uw >> 4;
             // slot = 2*axis + side; side 0: the owner (lower) voxel carries the label, 1: the upper one
             if (SLAB && rr - ftop9 < (uint32_t)RM) {
               vi[k] = __ldg(a.foreign + 4ull * ((size_t)(em0 + rr - ftop9) * vp.Efp + ef0 + lfx) + slot);
             } else {
-              const uint32_t idx = rr * RGN_WORDS + ((lfx >> 5) << 3) + slot;
+              const uint32_t idx = uw + ((lfx >> 5) << 3);
               const uint32_t g = rb[idx] + __popc(Rc[idx] & ((1u << (lfx & 31u)) - 1u));
               vi[k] = __ldg(a.perm + g) + voff;
             }
@@ -1213,6 +1218,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 4) k_emit(const VolParams vp
 
     // ---- vertices ----
     if (a.write_verts) {
+#pragma unroll 2
       for (uint32_t s = tid; s < h.nslots; s += NT) {
         const uint32_t rank = __ldg(a.perm + h.gbase + s);
         const uint32_t w = __ldg(a.vinfo + h.gbase + s);
