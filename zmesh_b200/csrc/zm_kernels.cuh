@@ -300,7 +300,6 @@ struct __align__(128) P1Smem {
   uint16_t actpre[NROWS];          // active voxels in earlier rows
   uint16_t pstage[MODE == 0 ? 2 : Caps<MODE>::VCAP];
   uint16_t rtoff[Caps<MODE>::RCAP];   // per record: first face row inside the (tile,label) block
-  uint8_t m8[TILE_VOX];            // slot mask of every voxel of a row with active voxels
   alignas(8) uint8_t pp8[NROWS][8];  // slots of the row in lower planes
 };
 static_assert(sizeof(P1Smem<u64, 1>) <= 227 * 1024 && sizeof(P1Smem<uint8_t, 1>) <= 227 * 1024, "dense mode must fit one SM");
@@ -422,40 +421,27 @@ __device__ __forceinline__ bool scan_tile(const VolParams& vp, P1Smem<L, MODE>& 
     const bool zm = am != 0;
     const bool okm = INTERIOR || em0 + j < vp.Em, nm1 = INTERIOR || em0 + j + 1 < vp.Em;
     const bool uniform = eq_row && eq_row2 && !nem;
-    bool act;
-    uint32_t m = 0;
+    // which of its three grid edges carry vertices (an edge with different endpoint labels)
+    bool pf = nef, pm = nem, ps = nes, act;
     if (INTERIOR) {
-      act = !uniform;
+      act = !uniform;  // (an edge with different labels makes the cube non-uniform)
     } else {
       const bool valid = okf && okm && oks;
-      if (valid) {
-        if (nf1 && nef) m |= (za ? 1u : 0u) | (zf ? 2u : 0u);
-        if (nm1 && nem) m |= (za ? 4u : 0u) | (zm ? 8u : 0u);
-        if (ns1 && nes) m |= (za ? 16u : 0u) | (zs ? 32u : 0u);
-      }
-      act = (m != 0u) || (valid && nf1 && nm1 && ns1 && !uniform);
+      pf = pf && valid && nf1; pm = pm && valid && nm1; ps = ps && valid && ns1;
+      act = (pf && (za || zf)) || (pm && (za || zm)) || (ps && (za || zs)) || (valid && nf1 && nm1 && ns1 && !uniform);
     }
     const uint32_t ab = __ballot_sync(FULL, act);
     uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
-    if (ab) {  // (m != 0 implies act)
+    if (ab) {  // (a voxel that owns a slot is active: rows without active voxels have empty planes)
       any = true;
-      if (INTERIOR) {
-        if (nef) m |= (za ? 1u : 0u) | (zf ? 2u : 0u);
-        if (nem) m |= (za ? 4u : 0u) | (zm ? 8u : 0u);
-        if (nes) m |= (za ? 16u : 0u) | (zs ? 32u : 0u);
-      }
-      S.m8[(ls * TM + j) * TF + lane] = (uint8_t)m;
-      if (__ballot_sync(FULL, m != 0u)) {
-        b0 = __ballot_sync(FULL, m & 1u); b1 = __ballot_sync(FULL, m & 2u);
-        b2 = __ballot_sync(FULL, m & 4u); b3 = __ballot_sync(FULL, m & 8u);
-        b4 = __ballot_sync(FULL, m & 16u); b5 = __ballot_sync(FULL, m & 32u);
-      }
+      b0 = __ballot_sync(FULL, pf && za); b1 = __ballot_sync(FULL, pf && zf);
+      b2 = __ballot_sync(FULL, pm && za); b3 = __ballot_sync(FULL, pm && zm);
+      b4 = __ballot_sync(FULL, ps && za); b5 = __ballot_sync(FULL, ps && zs);
     }
     if (lane == 0) {
       uint32_t* row = S.pl[ls * TM + j];
       *reinterpret_cast<uint4*>(row) = make_uint4(b0, b1, b2, b3);
-      *reinterpret_cast<uint4*>(row + 4) =
-          make_uint4(b4, b5, __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3) + __popc(b4) + __popc(b5), ab);
+      *reinterpret_cast<uint4*>(row + 4) = make_uint4(b4, b5, 0u, ab);
     }
     a = am; af = amf; as_ = ams;
     nef = nef2; nes = nes2; eq_row = eq_row2;
@@ -505,7 +491,7 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     const uint32_t c0 = __popc(q0.x), c1 = c0 + __popc(q0.y), c2 = c1 + __popc(q0.z), c3 = c2 + __popc(q0.w);
     const uint32_t c4 = c3 + __popc(q1.x);
     *reinterpret_cast<uint2*>(S.pp8[row]) = make_uint2((c0 << 8) | (c1 << 16) | (c2 << 24), c3 | (c4 << 8));
-    packed = q1.z | ((uint32_t)__popc(q1.w) << 16);
+    packed = (c4 + __popc(q1.y)) | ((uint32_t)__popc(q1.w) << 16);
   }
   uint32_t rinc = packed;
 #pragma unroll
@@ -558,8 +544,10 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
 #pragma unroll
     for (int n = 0; n < 8; ++n)
       c[n] = lab[((ls + corner_ds<CO>(n)) * RM + (lm + corner_dm<CO>(n))) * RFP + (lf + corner_df<CO>(n))];
-    const uint32_t m = S.m8[vidx];
-    const bool cube = (ef0 + lf + 1 < vp.Ef) && (em0 + lm + 1 < vp.Em) && (es0 + ls + 1 < vp.Es);
+    // slots exist only on edges whose upper voxel is inside the (extended) volume
+    const bool axf = ef0 + lf + 1 < vp.Ef, axm = em0 + lm + 1 < vp.Em, axs = es0 + ls + 1 < vp.Es;
+    const uint32_t amask = (axf ? 0x03u : 0u) | (axm ? 0x0Cu : 0u) | (axs ? 0x30u : 0u);
+    const bool cube = axf && axm && axs;
     const uint32_t row = vidx >> 5;
     const uint32_t ltf = (1u << lf) - 1u;
     const uint32_t rowpre = S.pl[row][6];
@@ -578,9 +566,11 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
       uint32_t nt = 0, mine = 0;
       if (have && label != 0) {
         if (cube) nt = __ldg(&TRI_COUNT_D[cs]);
-        mine = (((msk >> 0) & 1u) * 0x15u) | (((msk >> corner_plus_f<CO>()) & 1u) << 1) |
-               (((msk >> corner_plus_m<CO>()) & 1u) << 3) | (((msk >> corner_plus_s<CO>()) & 1u) << 5);
-        mine &= m;
+        // neighbours (+f, +m, +s) carrying this label: the voxel owns the lower-side slot of an edge when it
+        // carries the label and the neighbour does not, the upper-side slot when only the neighbour does
+        const uint32_t nb = ((msk >> corner_plus_f<CO>()) & 1u) | (((msk >> corner_plus_m<CO>()) & 1u) << 2) |
+                            (((msk >> corner_plus_s<CO>()) & 1u) << 4);
+        mine = ((msk & 1u) ? (0x15u & ~nb) : (nb << 1)) & amask;
       }
       const uint32_t nv = __popc(mine);
       bool work = (nv | nt) != 0u;
@@ -593,12 +583,15 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
       // and gives the record its first face row inside the (tile,label) block
       const uint32_t grp = __match_any_sync(FULL, work ? (uint32_t)hs : 0xFFFFFFFFu);
       const uint32_t glt = grp & ltm;
-      uint32_t totv, tott;
-      const uint32_t prev = group_prefix3(work ? nv : 0u, grp, glt, totv);
-      const uint32_t pret = group_prefix3(work ? nt : 0u, grp, glt, tott);
+      const uint32_t wv = work ? nv : 0u, wt = work ? nt : 0u;  // nv <= 3, nt <= 5
+      const uint32_t tot = __reduce_add_sync(grp, wv | (wt << 16));
+      const uint32_t v0 = __ballot_sync(FULL, wv & 1u), v1 = __ballot_sync(FULL, wv & 2u);
+      const uint32_t t0 = __ballot_sync(FULL, wt & 1u), t1 = __ballot_sync(FULL, wt & 2u), t2 = __ballot_sync(FULL, wt & 4u);
+      const uint32_t prev = __popc(v0 & glt) + 2u * __popc(v1 & glt);
+      const uint32_t pret = __popc(t0 & glt) + 2u * __popc(t1 & glt) + 4u * __popc(t2 & glt);
       const int leader = __ffs(grp) - 1;
       uint32_t old = 0;
-      if (work && lane == leader) old = atomicAdd(&S.lcnt[hs], totv | (tott << 16));
+      if (work && lane == leader) old = atomicAdd(&S.lcnt[hs], tot);
       old = __shfl_sync(FULL, old, leader);
       if (work && nv) {
         uint32_t r = (old & 0xFFFFu) + prev;
