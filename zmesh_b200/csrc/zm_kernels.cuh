@@ -1056,8 +1056,8 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 5) k_emit(const VolParams vp
                                                              const Pass2Args a) {
   constexpr uint32_t FULL = 0xffffffffu;
   __shared__ __align__(128) uint32_t R[2][RGN_PAD];   // TMA destinations: rowinfo of the region
-  __shared__ uint32_t rb[RGN_ROWS * RGN_WORDS];       // spatial id of the first slot of (row, segment, plane)
-  __shared__ __align__(16) TLEntry tls[TLC];
+  __shared__ uint32_t rb2[2][RGN_ROWS * RGN_WORDS];   // spatial id of the first slot of (row, segment, plane)
+  __shared__ __align__(16) TLEntry tls2[2][TLC];
   __shared__ __align__(16) TileHdr s_hdr[2];
   __shared__ u64 bar[2];
   __shared__ uint32_t s_tab[256 * CASE_TRIS];
@@ -1101,11 +1101,11 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 5) k_emit(const VolParams vp
 
   for (uint32_t it = 0; i < n; i += G, ++it) {
     const int cur = it & 1;
-    if (tid == 0 && i + G < n) {
-      s_hdr[cur ^ 1] = hnext;
-      issue(hnext, cur ^ 1);
-      if (i + 2 * G < n) hnext = load_hdr(a.hdr + i + 2 * G);
-    }
+    // All per-tile state is double buffered, so one barrier per tile suffices: passing barrier(it)
+    // means every thread has finished tile it-1, whose buffers tile it+1 may then overwrite.
+    if (tid == 0 && i + G < n) s_hdr[cur ^ 1] = hnext;
+    uint32_t* const rb = rb2[cur];
+    TLEntry* const tls = tls2[cur];
     TileHdr h;
     {
       union { uint4 q[2]; TileHdr h; } u;
@@ -1135,6 +1135,10 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 5) k_emit(const VolParams vp
       }
     }
     __syncthreads();
+    if (tid == 0 && i + G < n) {  // the region of the next tile lands while this one is processed
+      issue(hnext, cur ^ 1);
+      if (i + 2 * G < n) hnext = load_hdr(a.hdr + i + 2 * G);
+    }
 
     // ---- faces ----
     if (a.write_faces || NORMALS) {
@@ -1227,7 +1231,6 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 5) k_emit(const VolParams vp
         v[2] = __fmul_rn(p2, 0.5f);
       }
     }
-    __syncthreads();  // region buffer, slot bases, tl cache and header slot are free again
   }
 }
 
