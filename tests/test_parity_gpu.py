@@ -77,6 +77,17 @@ def test_codecs_roundtrip_on_gpu_mesh(Mesher):
   assert Mesh.from_precomputed(mesher.get(1, normals=True).to_precomputed()) != mesher.get(1, normals=True)
 
 
+def _blobs(shape, dtype, order):
+  """Background label 9 (non-zero: uniform tiles of a non-zero label) with a few boxes of other labels."""
+  rng = np.random.default_rng(7)
+  v = np.full(shape, 9, dtype=dtype)
+  for k in range(6):
+    lo = [int(rng.integers(0, s - 3)) for s in shape]
+    hi = [min(s, l + int(rng.integers(2, 12))) for s, l in zip(shape, lo)]
+    v[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]] = (0, 3, 4, 5, 2**31 + 5, 77)[k] if np.dtype(dtype).itemsize >= 4 else (0, 3, 4, 5, 200, 77)[k]
+  return np.asarray(v, order=order)
+
+
 SEEDED = [
   # name, volume factory, res, close
   ("crop128_F", lambda c: np.asfortranarray(c[100:228, 100:228, 100:228]), (4, 4, 40), False),
@@ -90,6 +101,11 @@ SEEDED = [
   ("thin_s", lambda c: random_volume((70, 40, 2), 5, np.uint32, 4, "F"), (1, 1, 1), True),
   ("tile_edges", lambda c: random_volume((33, 9, 9), 3, np.uint8, 5, "F"), (1, 1, 1), False),
   ("tile_exact", lambda c: random_volume((64, 16, 16), 7, np.uint16, 6, "F"), (1, 1, 1), False),
+  # mostly uniform volumes with a few blobs: the whole-region uniform test, with TMA (row pitch a multiple of
+  # 16 bytes) and with the plain-load staging path (70 * 2 bytes is not), with and without the `close` border
+  ("blobs_tma_close", lambda c: _blobs((96, 40, 40), np.uint32, "F"), (4, 4, 40), True),
+  ("blobs_plain_u16", lambda c: _blobs((70, 33, 41), np.uint16, "F"), (1, 2, 3), False),
+  ("blobs_plain_u64_C_close", lambda c: _blobs((37, 50, 67), np.uint64, "C"), (1, 1, 1), True),
 ]
 
 

@@ -10,7 +10,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzmesh_b200.so")
+LIB_PATH = os.environ.get("ZMESH_B200_LIB") or os.path.join(HERE, "libzmesh_b200.so")  # (override: development A/B builds)
 SOURCES = [os.path.join(HERE, "csrc", f) for f in ("zm_host.cu", "zm_kernels.cuh", "mc_tables.h")]
 HEADER = os.path.join(os.path.dirname(HERE), "include", "zmesh_b200.h")
 

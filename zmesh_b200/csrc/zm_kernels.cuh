@@ -733,7 +733,10 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
 
 // MODE 0: one CTA per tile (the hardware CTA scheduler overlaps the TMA wait of one tile with the
 // work of the others resident on the SM).  MODE 1: the queued dense tiles, two half tiles each.
-constexpr uint32_t PREFETCH_DISTANCE = 148 * 6;  // tiles ahead (in launch order) whose region is pulled into L2
+#ifndef ZM_PREFETCH_TILES
+#define ZM_PREFETCH_TILES (148 * 6)
+#endif
+constexpr uint32_t PREFETCH_DISTANCE = ZM_PREFETCH_TILES;  // tiles ahead (in launch order) whose region is pulled into L2 (0: off)
 template <typename L, bool CO, int MODE>
 __global__ void __launch_bounds__(NT, MODE == 0 ? (sizeof(L) == 8 ? 4 : 5) : 1)
 k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const Pass1Args o) {
@@ -748,7 +751,7 @@ k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const P
     if (tid == 0) {
       begin_tile(vp, &tmap, S, tile);
       uint32_t pt = tile + PREFETCH_DISTANCE;
-      if (vp.use_tma && pt < vp.ntf * vp.ntm * vp.nts) {
+      if (PREFETCH_DISTANCE != 0 && vp.use_tma && pt < vp.ntf * vp.ntm * vp.nts) {
         const uint32_t ptf = pt % vp.ntf;
         pt /= vp.ntf;
         int c0, c1, c2;
@@ -1050,9 +1053,16 @@ __device__ __forceinline__ TileHdr load_hdr(const TileHdr* p) {
 constexpr int RGN_ROWS = RM * RS;            // 81
 constexpr int RGN_WORDS = 2 * RI_WORDS;      // two row segments per region row
 constexpr int RGN_PAD = 1312;                // words per staged region buffer (5184 B rounded up to 128 B)
+#ifndef ZM_EMIT_CTAS
+#define ZM_EMIT_CTAS 5   // resident CTAs per SM the register allocation of k_emit is bounded for
+#endif
+#ifndef ZM_EMIT_UNROLL
+#define ZM_EMIT_UNROLL 1
+#endif
+constexpr int EMIT_UNROLL = ZM_EMIT_UNROLL;
 constexpr int TLC = 64;                      // tile-local labels whose tl entry is cached in shared memory
 template <bool CO, bool NORMALS, bool SLAB>
-__global__ void __launch_bounds__(NT, NORMALS ? 3 : 5) k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap,
+__global__ void __launch_bounds__(NT, NORMALS ? 3 : ZM_EMIT_CTAS) k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap,
                                                              const Pass2Args a) {
   constexpr uint32_t FULL = 0xffffffffu;
   __shared__ __align__(128) uint32_t R[2][RGN_PAD];   // TMA destinations: rowinfo of the region
@@ -1167,6 +1177,7 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : 5) k_emit(const VolParams vp
           for (uint32_t t = 0; t < nt; ++t) tlist[warp][tpre + t] = (uint8_t)((lane << 3) | t);
         }
         __syncwarp();
+#pragma unroll EMIT_UNROLL
         for (uint32_t q = lane; q < ntot; q += 32) {
           const uint32_t tr = tlist[warp][q];
           const uint32_t src = tr >> 3, t = tr & 7u;
