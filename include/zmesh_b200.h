@@ -172,7 +172,8 @@ typedef struct {
   uint32_t used_tma;   /* 1: tiles staged by TMA, 0: volume not 16-byte aligned, plain loads    */
   uint32_t launches_finalize;
   float ms_h2d, ms_classify, ms_scan, ms_total; /* CUDA-event times of the last zm_mesh          */
-  float ms_faces, ms_vertices, ms_finalize;     /* last zm_finalize / first zm_get (pass 2)      */
+  float ms_faces, ms_vertices, ms_finalize;     /* last zm_finalize / first zm_get (pass 2): the fused emit
+                                                   kernel, the normals normalisation (0 without normals), both */
   float reserved;
 } zm_stats_t;
 int zm_stats(zm_handle* h, zm_stats_t* out);
