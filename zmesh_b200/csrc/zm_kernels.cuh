@@ -331,7 +331,8 @@ __device__ __forceinline__ void begin_tile(const VolParams& vp, const CUtensorMa
   if (vp.use_tma) {
     int c0, c1, c2;
     stage_origin<L>(vp, tf, tm, ts, c0, c1, c2);
-    fence_proxy_async();
+    // MODE 1 re-stages a region whose memory lvb / cidx / tla were written to through the generic proxy
+    if (MODE == 1) fence_proxy_async();
     mbar_expect_tx(&S.mbar, (uint32_t)(sizeof(L) * RS * RM * P1Smem<L, MODE>::RFP));
     tma_load_3d(S.lab, tmap, &S.mbar, c0, c1, c2);
   }
@@ -1084,12 +1085,14 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : ZM_EMIT_CTAS) k_emit(const V
   uint32_t i = blockIdx.x;
   if (i >= n) return;
 
-  auto issue = [&](const TileHdr& h, int buf) {  // thread 0
+  // thread 0.  The region buffers are only ever READ through the generic proxy, and those reads are ordered
+  // before the refill by the CTA barrier, so no proxy fence is needed (a fence here costs the issuing warp a
+  // full memory barrier per tile: 24 % of the stall samples of k_emit on c5s).
+  auto issue = [&](const TileHdr& h, int buf) {
     uint32_t b = h.tile;
     const uint32_t tf = b % vp.ntf;
     b /= vp.ntf;
     const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
-    fence_proxy_async();
     mbar_expect_tx(&bar[buf], (uint32_t)(RGN_ROWS * RGN_WORDS * 4));
     tma_load_3d(R[buf], &rmap, &bar[buf], (int)(tf * RI_WORDS), (int)(tm * TM), (int)(ts * TS));
   };
