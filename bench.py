@@ -240,8 +240,19 @@ def main():
     G.build()
   if world > 1:
     torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-    dist.barrier()
+    # NCCL prints its version banner to stdout when the communicator is created (NCCL_DEBUG=VERSION on
+    # some boxes): keep stdout for the one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+      dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+      dist.barrier()
+      torch.cuda.synchronize()
+    finally:
+      sys.stdout.flush()
+      os.dup2(saved_stdout, 1)
+      os.close(saved_stdout)
   from zmesh_b200 import Mesher
 
   dev = local_rank
@@ -264,7 +275,10 @@ def main():
     mesher = Mesher(wl["res"], device=dev)
   vol = device_volume(name, wl, dev, zr if world > 1 else None)
   torch.cuda.synchronize()
-  stream = torch.cuda.current_stream()
+  # a dedicated (non-default) stream shared by the mesher's kernels and NCCL: the multi-GPU exchanges
+  # are then ordered on the device without host synchronisation
+  stream = torch.cuda.Stream(device=dev)
+  torch.cuda.set_stream(stream)
   mesher.set_stream(stream.cuda_stream)
 
   def step():
@@ -284,6 +298,8 @@ def main():
   for _ in range(args.warmup):
     st = step()
   barrier()
+  if sm is not None and getattr(sm, "timings", None):
+    sm.timings.clear()  # (ZM_SHARD_TIMING diagnostics: steady state only)
   acc = {k: 0.0 for k in ("ms_classify", "ms_scan", "ms_faces", "ms_vertices", "ms_total", "ms_finalize")}
   launches = 0
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -416,6 +432,8 @@ def main():
     }
     print(json.dumps(line), flush=True)
   if world > 1:
+    if rank == 0 and getattr(sm, "timings", None):
+      print("shard phase times (ms, summed over all mesh_slab calls):", {k: round(v, 2) for k, v in sm.timings.items()}, file=sys.stderr)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -712,8 +712,9 @@ int zm_export_plane(zm_handle* h, uint32_t* dst_device) {
   int rc = ensure_tl_fixed(h);
   if (rc != ZM_OK) return rc;
   Pass2Args a = pass2_args(h);
-  if (h->c_order) k_export_plane<true><<<h->n_work, NT_V, 0, h->stream>>>(h->vp, a, dst_device);
-  else k_export_plane<false><<<h->n_work, NT_V, 0, h->stream>>>(h->vp, a, dst_device);
+  const uint32_t grid = std::min<uint32_t>((h->n_work + NT_V / 32 - 1) / (NT_V / 32), (uint32_t)h->num_sms * 16u);
+  if (h->c_order) k_export_plane<true><<<grid, NT_V, 0, h->stream>>>(h->vp, a, dst_device);
+  else k_export_plane<false><<<grid, NT_V, 0, h->stream>>>(h->vp, a, dst_device);
   ZM_CUDA(h, cudaGetLastError());
   return ZM_OK;
 }

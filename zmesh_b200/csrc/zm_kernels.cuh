@@ -1249,23 +1249,26 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : ZM_EMIT_CTAS) k_emit(const V
 }
 
 // slab sharding: final (cross-shard) indices of the in-plane slots of this shard's FIRST plane, for
-// the shard below whose cubes reference them: dst[(em * Efp + ef) * 4 + slot] = label offset + rank
+// the shard below whose cubes reference them: dst[(em * Efp + ef) * 4 + slot] = label offset + rank.
+// One warp per work-list entry (grid-stride): entries of other planes cost one header load.
 constexpr int NT_V = 128;
 template <bool CO>
 __global__ void __launch_bounds__(NT_V) k_export_plane(const VolParams vp, const Pass2Args a, uint32_t* dst) {
-  const TileHdr h = load_hdr(a.hdr + blockIdx.x);
-  uint32_t b = h.tile;
-  const uint32_t tf = b % vp.ntf;
-  b /= vp.ntf;
-  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
-  if (ts != 0 || h.nslots == 0) return;
-  const TLEntry* tl = a.tl + h.tlbase;
-  for (uint32_t i = threadIdx.x; i < h.nslots; i += NT_V) {
-    const uint32_t w = __ldg(a.vinfo + h.gbase + i);
-    const uint32_t vidx = w & 0x7FFu, s6 = (w >> 11) & 7u, ci = w >> 14;
-    if ((vidx >> 8) != 0u || s6 >= 4u) continue;
-    const uint32_t ef = tf * TF + (vidx & 31u), em = tm * TM + ((vidx >> 5) & 7u);
-    dst[4ull * ((size_t)em * vp.Efp + ef) + s6] = (uint32_t)(tl[ci].a >> 32) + __ldg(a.perm + h.gbase + i);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t nwarps = gridDim.x * (NT_V / 32);
+  const uint32_t plane_tiles = vp.ntf * vp.ntm;
+  for (uint32_t w = blockIdx.x * (NT_V / 32) + (threadIdx.x >> 5); w < a.n_work; w += nwarps) {
+    const TileHdr h = load_hdr(a.hdr + w);
+    if (h.tile >= plane_tiles || h.nslots == 0) continue;  // not in the first tile layer
+    const uint32_t tf = h.tile % vp.ntf, tm = h.tile / vp.ntf;
+    const TLEntry* tl = a.tl + h.tlbase;
+    for (uint32_t i = lane; i < h.nslots; i += 32) {
+      const uint32_t v = __ldg(a.vinfo + h.gbase + i);
+      const uint32_t vidx = v & 0x7FFu, s6 = (v >> 11) & 7u, ci = v >> 14;
+      if ((vidx >> 8) != 0u || s6 >= 4u) continue;
+      const uint32_t ef = tf * TF + (vidx & 31u), em = tm * TM + ((vidx >> 5) & 7u);
+      dst[4ull * ((size_t)em * vp.Efp + ef) + s6] = (uint32_t)(tl[ci].a >> 32) + __ldg(a.perm + h.gbase + i);
+    }
   }
 }
 

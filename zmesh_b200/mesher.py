@@ -201,6 +201,11 @@ class Mesher:
   def set_stream(self, cuda_stream):
     """Queue all work on a caller-owned CUDA stream (integer cudaStream_t); None restores the own one."""
     self._check(self._lib.zm_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
+    self._user_stream = int(cuda_stream) if cuda_stream else None
+
+  def stream_handle(self):
+    """The caller-owned stream set by set_stream (integer cudaStream_t), or None for the handle's own."""
+    return getattr(self, "_user_stream", None)
 
   def _mesh_device(self, obj, cai, close: bool):
     shape = tuple(int(s) for s in cai["shape"])

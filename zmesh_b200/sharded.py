@@ -61,26 +61,38 @@ def offsets_from_directories(labels_by_rank, nv_by_rank, rank: int):
   return out.astype(np.uint32)
 
 
+_dir_capacity = 256  # rows of the fixed-size exchange buffer; grows to fit (every rank sees every size)
+
+
 def all_gather_directories(labels, nv, group=None, device=None):
-  """All-gather of variable-length (label, count) directories; works with gloo (CPU) and NCCL."""
+  """All-gather of variable-length (label, count) directories; works with gloo (CPU) and NCCL.
+  One collective in the steady state: row 0 of every rank's fixed-capacity buffer carries its
+  length; if any directory does not fit, all ranks see that and repeat with a larger buffer."""
+  global _dir_capacity
   import torch
   import torch.distributed as dist
   world = dist.get_world_size(group)
   dev = device if device is not None else "cpu"
-  n = torch.tensor([labels.size], dtype=torch.int64, device=dev)
-  sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-  dist.all_gather(sizes, n, group=group)
-  sizes = [int(s.item()) for s in sizes]
-  m = max(max(sizes), 1)
-  buf = torch.zeros((m, 2), dtype=torch.int64, device=dev)
-  if labels.size:
-    both = np.stack([labels.astype(np.uint64).view(np.int64), nv.astype(np.uint64).view(np.int64)], axis=1)
-    buf[:labels.size] = torch.from_numpy(both).to(dev)
-  outs = [torch.zeros_like(buf) for _ in range(world)]
-  dist.all_gather(outs, buf, group=group)
+  n = int(labels.size)
+  while True:
+    cap = max(_dir_capacity, 1)
+    host = np.zeros((cap + 1, 2), dtype=np.int64)
+    host[0, 0] = n
+    m = min(n, cap)
+    if m:
+      host[1:1 + m, 0] = labels[:m].astype(np.uint64).view(np.int64)
+      host[1:1 + m, 1] = nv[:m].astype(np.uint64).view(np.int64)
+    buf = torch.from_numpy(host).to(dev)
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    allh = torch.stack(outs).cpu().numpy()  # one device->host copy
+    sizes = [int(allh[q, 0, 0]) for q in range(world)]
+    if max(sizes) <= cap:
+      break
+    _dir_capacity = 1 << int(max(sizes) - 1).bit_length()
   ls, ns = [], []
   for q in range(world):
-    a = outs[q][:sizes[q]].cpu().numpy()
+    a = allh[q, 1:1 + sizes[q]]
     ls.append(a[:, 0].copy().view(np.uint64))
     ns.append(a[:, 1].copy().view(np.uint64))
   return ls, ns
@@ -121,21 +133,29 @@ class ShardedMesher:
     import torch.distributed as dist
     cube_lo, cube_hi, in_lo, in_hi, last = self.planes(full_extent, close)
     m = self.mesher
+    tm = self._timer()
     m.mesh_slab(data, full_extent, buf_lo, cube_lo, cube_hi, last, close=close)
+    tm("pass1")
     labels, nv, nt = m.directory()
     dev = f"cuda:{self.device}"
     ls, ns = all_gather_directories(labels, nv, self.group, dev)
+    tm("all_gather")
     m.set_label_offsets(labels, offsets_from_directories(ls, ns, self.rank))
+    tm("offsets")
     self._dir = (labels, nv, nt)
-    # boundary plane: rank r+1 -> rank r
+    # boundary plane: rank r+1 -> rank r.  When the mesher queues its kernels on torch's current stream
+    # (Mesher.set_stream, as bench.py does) the export kernel, the NCCL transfer and pass 2 are ordered
+    # on the device and no host synchronisation is needed.
     n = m.plane_elems()
     ops = []
     stream = torch.cuda.current_stream()
+    same_stream = m.stream_handle() == int(stream.cuda_stream)
     if self.rank > 0:
       if self._plane_send is None or self._plane_send.numel() != n:
         self._plane_send = torch.empty(n, dtype=torch.int32, device=dev)
       m.export_plane(self._plane_send.data_ptr())
-      m.sync()
+      if not same_stream:
+        m.sync()
       ops.append(dist.P2POp(dist.isend, self._plane_send, self.rank - 1, group=self.group))
     if not last:
       if self._plane_recv is None or self._plane_recv.numel() != n:
@@ -143,12 +163,34 @@ class ShardedMesher:
       ops.append(dist.P2POp(dist.irecv, self._plane_recv, self.rank + 1, group=self.group))
     if ops:
       for w in dist.batch_isend_irecv(ops):
-        w.wait()
-      stream.synchronize()
+        w.wait()  # makes the current stream wait for the transfer (no host block)
+      if not same_stream:
+        stream.synchronize()
     m.set_foreign_plane(self._plane_recv.data_ptr() if not last else None)
+    tm("plane_exchange")
+    out = None
     if finalize:
-      return m.finalize(normals=False, voxel_centered=voxel_centered)
-    return None
+      out = m.finalize(normals=False, voxel_centered=voxel_centered)
+      tm("pass2")
+    return out
+
+  def _timer(self):
+    """Per-phase wall times in self.timings (ms, accumulated) when ZM_SHARD_TIMING is set; each phase is
+    closed with a device synchronisation, so this perturbs the overlap it measures."""
+    import os
+    if not os.environ.get("ZM_SHARD_TIMING"):
+      return lambda name: None
+    import time
+    import torch
+    self.timings = getattr(self, "timings", {})
+    t = [time.perf_counter()]
+
+    def mark(name):
+      torch.cuda.synchronize()
+      now = time.perf_counter()
+      self.timings[name] = self.timings.get(name, 0.0) + (now - t[0]) * 1e3
+      t[0] = now
+    return mark
 
   def local_part(self, label, voxel_centered: bool = False):
     """(vertices, faces) this rank holds for `label` (faces carry cross-rank indices) or None."""
