@@ -320,13 +320,26 @@ __device__ __forceinline__ void stage_origin(const VolParams& vp, uint32_t tf, u
   c2 = (int)(ts * TS) + vp.s_shift;
 }
 
-// thread 0: publish the coordinates of `tile` and (TMA path) start the load of its region
+// Launch order of the MODE 0 tiles: f fastest, then a group of TM_GROUP tile rows, then ALL s layers, then
+// the next group.  The halo plane a tile shares with its s-neighbour is then re-read ntf * TM_GROUP tiles
+// later (8 MB of labels for c5) instead of ntf * ntm tiles later (268 MB > L2): ncu measured 12.6 % more
+// DRAM reads than the volume with the plain order.
+constexpr uint32_t TM_GROUP = 8;
+__device__ __forceinline__ void launch_order_coords(const VolParams& vp, uint32_t lin, uint32_t& tf, uint32_t& tm, uint32_t& ts) {
+  const uint32_t per_group = vp.ntf * TM_GROUP * vp.nts;
+  const uint32_t g = lin / per_group;
+  uint32_t rem = lin - g * per_group;
+  const uint32_t rows = min(TM_GROUP, vp.ntm - g * TM_GROUP);  // the last group may be short
+  tf = rem % vp.ntf;
+  rem /= vp.ntf;
+  tm = g * TM_GROUP + rem % rows;
+  ts = rem / rows;
+}
+
+// thread 0: publish the coordinates of a tile and (TMA path) start the load of its region
 template <typename L, int MODE>
-__device__ __forceinline__ void begin_tile(const VolParams& vp, const CUtensorMap* tmap, P1Smem<L, MODE>& S, uint32_t tile) {
-  uint32_t b = tile;
-  const uint32_t tf = b % vp.ntf;
-  b /= vp.ntf;
-  const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
+__device__ __forceinline__ void begin_tile(const VolParams& vp, const CUtensorMap* tmap, P1Smem<L, MODE>& S, uint32_t tf,
+                                           uint32_t tm, uint32_t ts) {
   S.tc[0] = tf; S.tc[1] = tm; S.tc[2] = ts;
   if (vp.use_tma) {
     int c0, c1, c2;
@@ -748,20 +761,22 @@ k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const P
     fence_mbar_init();
   }
   if (MODE == 0) {
-    const uint32_t tile = blockIdx.x;
     if (tid == 0) {
-      begin_tile(vp, &tmap, S, tile);
-      uint32_t pt = tile + PREFETCH_DISTANCE;
+      uint32_t tf0, tm0, ts0;
+      launch_order_coords(vp, blockIdx.x, tf0, tm0, ts0);
+      begin_tile(vp, &tmap, S, tf0, tm0, ts0);
+      const uint32_t pt = blockIdx.x + PREFETCH_DISTANCE;
       if (PREFETCH_DISTANCE != 0 && vp.use_tma && pt < vp.ntf * vp.ntm * vp.nts) {
-        const uint32_t ptf = pt % vp.ntf;
-        pt /= vp.ntf;
+        uint32_t ptf, ptm, pts;
+        launch_order_coords(vp, pt, ptf, ptm, pts);
         int c0, c1, c2;
-        stage_origin<L>(vp, ptf, pt % vp.ntm, pt / vp.ntm, c0, c1, c2);
+        stage_origin<L>(vp, ptf, ptm, pts, c0, c1, c2);
         tma_prefetch_3d(&tmap, c0, c1, c2);
       }
     }
     __syncthreads();  // mbarrier initialised, coordinates published
     const uint32_t tf = S.tc[0], tm = S.tc[1], ts = S.tc[2];
+    const uint32_t tile = tf + vp.ntf * (tm + vp.ntm * ts);  // canonical index (work list, dense list)
     if (vp.use_tma) {
       mbar_wait(&S.mbar, 0);  // every thread waits itself: the TMA writes are visible to it afterwards
     } else {
@@ -778,7 +793,12 @@ k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const P
       const uint32_t tile = o.dense_list[i];
       for (int half = 0; half < Caps<MODE>::HALVES; ++half) {
         const int nh = TS / Caps<MODE>::HALVES, h0 = half * nh;
-        if (tid == 0) begin_tile(vp, &tmap, S, tile);  // (the region is staged again: lvb / cidx of the first half overwrote it)
+        if (tid == 0) {  // (the region is staged again: lvb / cidx of the first half overwrote it)
+          uint32_t b = tile;
+          const uint32_t tf0 = b % vp.ntf;
+          b /= vp.ntf;
+          begin_tile(vp, &tmap, S, tf0, b % vp.ntm, b / vp.ntm);
+        }
         __syncthreads();
         const uint32_t tf = S.tc[0], tm = S.tc[1], ts = S.tc[2];
         if (vp.use_tma) {
