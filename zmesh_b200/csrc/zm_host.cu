@@ -523,9 +523,9 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
       if (!make_rowinfo_map(&rmap, h->d_rowinfo.p, h->vp)) return fail(h, ZM_ERR_CUDA, "cuTensorMapEncodeTiled(rowinfo) failed");
       pass2_fn fn = emit_kernel(h->c_order, need_normals, h->slab_mode);
       int per_sm = 0;
-      ZM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, NT, 0));
+      ZM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, EMIT_THREADS, 0));
       const uint32_t grid = std::min<uint32_t>(h->n_work, (uint32_t)(h->num_sms * std::max(per_sm, 1)));
-      fn<<<grid, NT, 0, st>>>(h->vp, rmap, a);
+      fn<<<grid, EMIT_THREADS, 0, st>>>(h->vp, rmap, a);
       ZM_CUDA(h, cudaGetLastError());
       ++launches;
     }

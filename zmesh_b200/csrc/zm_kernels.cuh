@@ -1063,87 +1063,127 @@ __device__ __forceinline__ TileHdr load_hdr(const TileHdr* p) {
   return u.h;
 }
 
-// k_emit: persistent CTAs over the work list of non-empty (half) tiles.  Per tile one TMA load
-// brings the rowinfo of the (TM+1)(TS+1) rows x 2 segments whose slots the tile's cubes can
-// reference (the load of the CTA's next tile is in flight meanwhile); 162 threads turn it into
-// per-(row, segment, plane) slot bases.  Records are read 32 per warp, their triangles expanded so
-// that every lane owns one triangle: three slot lookups (two shared loads + popc -> perm) and three
-// 4-byte stores, consecutive lanes writing consecutive 12-byte rows.  Then one thread per vertex
-// slot of the tile writes the float32 vertex in its final form (reference: _normalize_mesh
-// zmesh/_zmesh.pyx:423-433: three separately rounded float32 operations, no FMA).
+// k_emit: persistent, warp-specialised CTAs over the work list of non-empty (half) tiles.
+//   producer warp : walks the CTA's tiles EMIT_STAGES ahead of the consumers.  Per tile: one TMA load
+//                   brings the rowinfo of the (TM+1)(TS+1) rows x 2 segments whose slots the tile's
+//                   cubes can reference; the tile's header and tl entries are copied to shared memory
+//                   and the region is turned into per-(row, segment, plane) slot bases.
+//   consumer warps: no CTA barrier -- a warp waits for a stage (mbarrier `ready`), does its share of the
+//                   tile and releases the stage (mbarrier `empty`), so a slow warp never stalls the others.
+//                   Records are read 32 per warp (next batch prefetched), their triangles expanded so that
+//                   every lane owns one triangle: three slot lookups (two shared loads + popc -> perm) and
+//                   three 4-byte stores, consecutive lanes writing consecutive 12-byte rows.  Then one
+//                   thread per vertex slot writes the float32 vertex in its final form (reference:
+//                   _normalize_mesh zmesh/_zmesh.pyx:423-433: three separately rounded operations, no FMA).
 constexpr int RGN_ROWS = RM * RS;            // 81
 constexpr int RGN_WORDS = 2 * RI_WORDS;      // two row segments per region row
 constexpr int RGN_PAD = 1312;                // words per staged region buffer (5184 B rounded up to 128 B)
+// (consumer warps, stages, CTAs per SM) measured on B200, c1 / c5s k_emit ms: (7,2,5) 0.952 / 0.216, (8,2,4) 0.969 /
+// 0.221, (8,3,4) 0.988 / 0.226, (12,3,3) 0.987 / 0.224, (16,3,2) 0.988 / 0.225; CTA-barrier version 1.00 / 0.228
 #ifndef ZM_EMIT_CTAS
 #define ZM_EMIT_CTAS 5   // resident CTAs per SM the register allocation of k_emit is bounded for
 #endif
-#ifndef ZM_EMIT_UNROLL
-#define ZM_EMIT_UNROLL 1
+#ifndef ZM_EMIT_CONSUMERS
+#define ZM_EMIT_CONSUMERS 7
 #endif
-constexpr int EMIT_UNROLL = ZM_EMIT_UNROLL;
+#ifndef ZM_EMIT_STAGES
+#define ZM_EMIT_STAGES 2
+#endif
+constexpr int EMIT_NC = ZM_EMIT_CONSUMERS;           // consumer warps
+constexpr int EMIT_ST = ZM_EMIT_STAGES;              // tiles in flight per CTA
+constexpr int EMIT_THREADS = 32 * (EMIT_NC + 1);     // + the producer warp
 constexpr int TLC = 64;                      // tile-local labels whose tl entry is cached in shared memory
+
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <bool CO, bool NORMALS, bool SLAB>
-__global__ void __launch_bounds__(NT, NORMALS ? 3 : ZM_EMIT_CTAS) k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap,
-                                                             const Pass2Args a) {
+__global__ void __launch_bounds__(EMIT_THREADS, NORMALS ? 3 : ZM_EMIT_CTAS)
+k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2Args a) {
   constexpr uint32_t FULL = 0xffffffffu;
-  __shared__ __align__(128) uint32_t R[2][RGN_PAD];   // TMA destinations: rowinfo of the region
-  __shared__ uint32_t rb2[2][RGN_ROWS * RGN_WORDS];   // spatial id of the first slot of (row, segment, plane)
-  __shared__ __align__(16) TLEntry tls2[2][TLC];
-  __shared__ __align__(16) TileHdr s_hdr[2];
-  __shared__ u64 bar[2];
+  __shared__ __align__(128) uint32_t R[EMIT_ST][RGN_PAD];       // TMA destinations: rowinfo of the region
+  __shared__ uint32_t rbs[EMIT_ST][RGN_ROWS * RGN_WORDS];       // spatial id of the first slot of (row, segment, plane)
+  __shared__ __align__(16) TLEntry tlss[EMIT_ST][TLC];
+  __shared__ __align__(16) TileHdr s_hdr[EMIT_ST];
+  __shared__ u64 full[EMIT_ST], ready[EMIT_ST], empty[EMIT_ST];
   __shared__ uint32_t s_tab[256 * CASE_TRIS];
   __shared__ uint8_t s_tricount[256];
-  __shared__ u64 rf[NW][32];              // per record of the warp's batch: first face row
-  __shared__ u64 rv[NW][32];              //                                  first vertex row of the label
-  __shared__ uint32_t ru[NW][32];         //                                  region row * 16 | f << 11 | case << 16
-  __shared__ uint32_t rvo[NW][32];        //                                  index offset of the label (earlier shards)
-  __shared__ uint8_t tlist[NW][160];      // triangles of the batch: record lane << 3 | t
+  __shared__ u64 rf[EMIT_NC][32];              // per record of the warp's batch: first face row
+  __shared__ u64 rv[NORMALS ? EMIT_NC : 1][32];  //                                first vertex row of the label
+  __shared__ uint32_t ru[EMIT_NC][32];         //                                  region row * 16 | f << 11 | case << 16
+  __shared__ uint32_t rvo[SLAB ? EMIT_NC : 1][32];  //                             index offset of the label (earlier shards)
+  __shared__ uint8_t tlist[EMIT_NC][160];      // triangles of the batch: record lane << 3 | t
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t ltm = (1u << lane) - 1u;
   const uint32_t n = a.n_work, G = gridDim.x;
-  uint32_t i = blockIdx.x;
-  if (i >= n) return;
+  const uint32_t first = blockIdx.x;
+  if (first >= n) return;
+  const uint32_t ntile = (n - first + G - 1) / G;  // tiles of this CTA: first, first + G, ...
 
-  // thread 0.  The region buffers are only ever READ through the generic proxy, and those reads are ordered
-  // before the refill by the CTA barrier, so no proxy fence is needed (a fence here costs the issuing warp a
-  // full memory barrier per tile: 24 % of the stall samples of k_emit on c5s).
-  auto issue = [&](const TileHdr& h, int buf) {
-    uint32_t b = h.tile;
-    const uint32_t tf = b % vp.ntf;
-    b /= vp.ntf;
-    const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
-    mbar_expect_tx(&bar[buf], (uint32_t)(RGN_ROWS * RGN_WORDS * 4));
-    tma_load_3d(R[buf], &rmap, &bar[buf], (int)(tf * RI_WORDS), (int)(tm * TM), (int)(ts * TS));
-  };
-
-  TileHdr hnext;
-  hnext.tile = 0;
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    for (int s = 0; s < EMIT_ST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&ready[s], 1);
+      mbar_init(&empty[s], EMIT_NC);
+    }
     fence_mbar_init();
-    const TileHdr h0 = load_hdr(a.hdr + i);
-    s_hdr[0] = h0;
-    issue(h0, 0);
-    if (i + G < n) hnext = load_hdr(a.hdr + i + G);
   }
-  s_tricount[tid] = TRI_COUNT_D[tid];
-  for (int j = tid; j < 256 * CASE_TRIS; j += NT) s_tab[j] = CASE_TAB_D[CO ? 1 : 0][j];
+  for (int j = tid; j < 256; j += EMIT_THREADS) s_tricount[j] = TRI_COUNT_D[j];
+  for (int j = tid; j < 256 * CASE_TRIS; j += EMIT_THREADS) s_tab[j] = CASE_TAB_D[CO ? 1 : 0][j];
   __syncthreads();
 
-  for (uint32_t it = 0; i < n; i += G, ++it) {
-    const int cur = it & 1;
-    // All per-tile state is double buffered, so one barrier per tile suffices: passing barrier(it)
-    // means every thread has finished tile it-1, whose buffers tile it+1 may then overwrite.
-    if (tid == 0 && i + G < n) s_hdr[cur ^ 1] = hnext;
-    uint32_t* const rb = rb2[cur];
-    TLEntry* const tls = tls2[cur];
+  if (warp == EMIT_NC) {
+    // ================= producer warp =================
+    TileHdr hn;
+    hn.tile = 0; hn.nlab = 0; hn.tlbase = 0;
+    if (lane == 0) hn = load_hdr(a.hdr + first);
+    for (uint32_t it = 0; it < ntile; ++it) {
+      const int s = it % EMIT_ST;
+      const uint32_t k = it / EMIT_ST;  // k-th use of stage s
+      if (k > 0) mbar_wait(&empty[s], (k - 1) & 1u);  // every consumer warp has released the stage
+      if (lane == 0) {
+        s_hdr[s] = hn;
+        uint32_t b = hn.tile;
+        const uint32_t tf = b % vp.ntf;
+        b /= vp.ntf;
+        // The region buffers are only ever READ through the generic proxy and those reads are ordered before
+        // this refill by the `empty` mbarrier, so no proxy fence is needed.
+        mbar_expect_tx(&full[s], (uint32_t)(RGN_ROWS * RGN_WORDS * 4));
+        tma_load_3d(R[s], &rmap, &full[s], (int)(tf * RI_WORDS), (int)((b % vp.ntm) * TM), (int)((b / vp.ntm) * TS));
+      }
+      const uint32_t nlab = __shfl_sync(FULL, (uint32_t)hn.nlab, 0), tlbase = __shfl_sync(FULL, hn.tlbase, 0);
+      if (lane == 0 && it + 1 < ntile) hn = load_hdr(a.hdr + first + (size_t)(it + 1) * G);  // next header in flight
+      for (uint32_t j = lane; j < nlab && j < (uint32_t)TLC; j += 32) tlss[s][j] = a.tl[tlbase + j];
+      mbar_wait(&full[s], k & 1u);  // every lane waits itself: the TMA writes are visible to it afterwards
+      for (int e = lane; e < RGN_ROWS * 2; e += 32) {
+        const uint32_t* seg = R[s] + e * RI_WORDS;
+        uint32_t run = seg[6];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          rbs[s][e * RI_WORDS + p] = run;
+          run += __popc(seg[p]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[s]);  // (release: header, tl cache and slot bases are visible to the waiters)
+    }
+    return;
+  }
+
+  // ================= consumer warps =================
+  const int cw = warp;
+  for (uint32_t it = 0; it < ntile; ++it) {
+    const int s = it % EMIT_ST;
+    const uint32_t k = it / EMIT_ST;
+    mbar_wait(&ready[s], k & 1u);
+    mbar_wait(&full[s], k & 1u);  // (already complete: makes the TMA-written region visible to this thread)
     TileHdr h;
     {
       union { uint4 q[2]; TileHdr h; } u;
-      u.q[0] = reinterpret_cast<const uint4*>(&s_hdr[cur])[0];
-      u.q[1] = reinterpret_cast<const uint4*>(&s_hdr[cur])[1];
+      u.q[0] = reinterpret_cast<const uint4*>(&s_hdr[s])[0];
+      u.q[1] = reinterpret_cast<const uint4*>(&s_hdr[s])[1];
       h = u.h;
     }
     uint32_t b = h.tile;
@@ -1151,38 +1191,23 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : ZM_EMIT_CTAS) k_emit(const V
     b /= vp.ntf;
     const uint32_t tm = b % vp.ntm, ts = b / vp.ntm;
     const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
-    const uint32_t* Rc = R[cur];
+    const uint32_t* const Rc = R[s];
+    const uint32_t* const rb = rbs[s];
+    const TLEntry* const tls = tlss[s];
     // slab sharding: region rows [ftop9, ftop9 + RM) lie on the plane owned by the next shard
     uint32_t ftop9 = 0xFFFFu;
     if (SLAB && vp.Es_own < vp.Es && vp.Es_own >= es0 && vp.Es_own - es0 < (uint32_t)RS) ftop9 = (vp.Es_own - es0) * RM;
-
-    for (uint32_t j = tid; j < h.nlab && j < (uint32_t)TLC; j += NT) tls[j] = a.tl[h.tlbase + j];
-    mbar_wait(&bar[cur], (it >> 1) & 1u);
-    if (tid < RGN_ROWS * 2) {
-      const uint32_t* seg = Rc + tid * RI_WORDS;
-      uint32_t run = seg[6];
-#pragma unroll
-      for (int s = 0; s < 6; ++s) {
-        rb[tid * RI_WORDS + s] = run;
-        run += __popc(seg[s]);
-      }
-    }
-    __syncthreads();
-    if (tid == 0 && i + G < n) {  // the region of the next tile lands while this one is processed
-      issue(hnext, cur ^ 1);
-      if (i + 2 * G < n) hnext = load_hdr(a.hdr + i + 2 * G);
-    }
 
     // ---- faces ----
     if (a.write_faces || NORMALS) {
       const uint32_t nrec = h.nrec;
       const u64* recp = a.rec + h.recbase;
-      uint32_t base = warp * 32;
+      uint32_t base = cw * 32;
       u64 wnext = base + lane < nrec ? __ldg(recp + base + lane) : 0ull;
-      for (; base < nrec; base += NT) {
+      for (; base < nrec; base += EMIT_NC * 32) {
         const bool valid = base + lane < nrec;
         const u64 w64 = wnext;
-        wnext = base + NT + lane < nrec ? __ldg(recp + base + NT + lane) : 0ull;  // next batch in flight during this one
+        wnext = base + EMIT_NC * 32 + lane < nrec ? __ldg(recp + base + EMIT_NC * 32 + lane) : 0ull;  // next batch in flight
         const uint32_t w = (uint32_t)w64;
         const uint32_t vidx = w & 0x7FFu, cs = (w >> 11) & 0xFFu, ci = w >> 19;
         const uint32_t nt = valid ? s_tricount[cs] : 0u;
@@ -1193,48 +1218,47 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : ZM_EMIT_CTAS) k_emit(const V
           if (ci < (uint32_t)TLC) e = tls[ci];
           else e = a.tl[h.tlbase + ci];
           const uint32_t lf = vidx & 31u, lm = (vidx >> 5) & 7u, ls = vidx >> 8;
-          ru[warp][lane] = ((ls * RM + lm) << 4) | (lf << 11) | (cs << 16);
-          rf[warp][lane] = e.b + (uint32_t)(w64 >> 32);
-          if (SLAB) rvo[warp][lane] = (uint32_t)(e.a >> 32);
-          if (NORMALS) rv[warp][lane] = e.a & 0xFFFFFFFFull;
-          for (uint32_t t = 0; t < nt; ++t) tlist[warp][tpre + t] = (uint8_t)((lane << 3) | t);
+          ru[cw][lane] = ((ls * RM + lm) << 4) | (lf << 11) | (cs << 16);
+          rf[cw][lane] = e.b + (uint32_t)(w64 >> 32);
+          if (SLAB) rvo[cw][lane] = (uint32_t)(e.a >> 32);
+          if (NORMALS) rv[cw][lane] = e.a & 0xFFFFFFFFull;
+          for (uint32_t t = 0; t < nt; ++t) tlist[cw][tpre + t] = (uint8_t)((lane << 3) | t);
         }
         __syncwarp();
-#pragma unroll EMIT_UNROLL
         for (uint32_t q = lane; q < ntot; q += 32) {
-          const uint32_t tr = tlist[warp][q];
+          const uint32_t tr = tlist[cw][q];
           const uint32_t src = tr >> 3, t = tr & 7u;
-          const uint32_t uc = ru[warp][src];
+          const uint32_t uc = ru[cw][src];
           const uint32_t u0 = uc & 0x7FFu, lf0 = (uc >> 11) & 31u;
           const uint32_t tab = s_tab[(uc >> 16) * CASE_TRIS + t];
-          const uint32_t voff = SLAB ? rvo[warp][src] : 0u;
+          const uint32_t voff = SLAB ? rvo[cw][src] : 0u;
           uint32_t vi[3];
           float p[3][3];
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const uint32_t en = (tab >> (9 * k)) & 0x1FFu;
+          for (int c = 0; c < 3; ++c) {
+            const uint32_t en = (tab >> (9 * c)) & 0x1FFu;
             const uint32_t lfx = lf0 + (en >> 8), slot = en & 7u;
             const uint32_t uw = u0 + (en & 0xFFu);  // word of (row, plane) in the first segment
             const uint32_t rr = uw >> 4;
             // slot = 2*axis + side; side 0: the owner (lower) voxel carries the label, 1: the upper one
             if (SLAB && rr - ftop9 < (uint32_t)RM) {
-              vi[k] = __ldg(a.foreign + 4ull * ((size_t)(em0 + rr - ftop9) * vp.Efp + ef0 + lfx) + slot);
+              vi[c] = __ldg(a.foreign + 4ull * ((size_t)(em0 + rr - ftop9) * vp.Efp + ef0 + lfx) + slot);
             } else {
               const uint32_t idx = uw + ((lfx >> 5) << 3);
               const uint32_t g = rb[idx] + __popc(Rc[idx] & ((1u << (lfx & 31u)) - 1u));
-              vi[k] = __ldg(a.perm + g) + voff;
+              vi[c] = __ldg(a.perm + g) + voff;
             }
             if (NORMALS) {
               const uint32_t rs_ = (rr * 57u) >> 9;  // rr / 9 for rr < 90
-              slot_position<CO>(vp, a, ef0 + lfx, em0 + rr - rs_ * RM, es0 + rs_, slot >> 1, p[k][0], p[k][1], p[k][2]);
+              slot_position<CO>(vp, a, ef0 + lfx, em0 + rr - rs_ * RM, es0 + rs_, slot >> 1, p[c][0], p[c][1], p[c][2]);
             }
           }
           if (a.write_faces) {
-            uint32_t* f = a.faces + 3ull * (rf[warp][src] + t);
+            uint32_t* f = a.faces + 3ull * (rf[cw][src] + t);
             f[0] = vi[0]; f[1] = vi[1]; f[2] = vi[2];
           }
           if (NORMALS) {
-            float* nb = a.normals + 3ull * rv[warp][src];
+            float* nb = a.normals + 3ull * rv[cw][src];
             float* d0 = nb + 3ull * (vi[0] - voff);
             float* d1 = nb + 3ull * (vi[1] - voff);
             float* d2 = nb + 3ull * (vi[2] - voff);
@@ -1250,9 +1274,9 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : ZM_EMIT_CTAS) k_emit(const V
     // ---- vertices ----
     if (a.write_verts) {
 #pragma unroll 2
-      for (uint32_t s = tid; s < h.nslots; s += NT) {
-        const uint32_t rank = __ldg(a.perm + h.gbase + s);
-        const uint32_t w = __ldg(a.vinfo + h.gbase + s);
+      for (uint32_t v_ = tid; v_ < h.nslots; v_ += EMIT_NC * 32) {
+        const uint32_t rank = __ldg(a.perm + h.gbase + v_);
+        const uint32_t w = __ldg(a.vinfo + h.gbase + v_);
         const uint32_t vidx = w & 0x7FFu, s6 = (w >> 11) & 7u, ci = w >> 14;
         const u64 ea = ci < (uint32_t)TLC ? tls[ci].a : a.tl[h.tlbase + ci].a;
         const u64 dst = (ea & 0xFFFFFFFFull) + rank;
@@ -1265,6 +1289,8 @@ __global__ void __launch_bounds__(NT, NORMALS ? 3 : ZM_EMIT_CTAS) k_emit(const V
         v[2] = __fmul_rn(p2, 0.5f);
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the stage
   }
 }
 
