@@ -303,8 +303,8 @@ def main():
   sm = None
   if world > 1:
     # z-slab sharding (zmesh_b200/sharded.py): rank r reads its cube planes + one halo plane
-    if wl["order"] != "F" or wl["normals"]:
-      raise SystemExit("multi-GPU bench: Fortran-order workloads without normals only (c1, c5, c5s)")
+    if wl["order"] != "F":
+      raise SystemExit("multi-GPU bench: Fortran-order workloads only (c1, c4, c5, c5s)")
     from zmesh_b200.sharded import ShardedMesher
     sm = ShardedMesher(wl["res"], device=dev)
     _, _, in_lo, in_hi, _ = sm.planes(shape[2], wl["close"])
@@ -323,7 +323,7 @@ def main():
 
   def step():
     if world > 1:
-      sm.mesh_slab(vol, shape[2], zr[0], close=wl["close"], finalize=True, voxel_centered=wl["vc"])
+      sm.mesh_slab(vol, shape[2], zr[0], close=wl["close"], finalize=True, voxel_centered=wl["vc"], normals=wl["normals"])
     else:
       mesher.mesh(vol, close=wl["close"])
       mesher.finalize(normals=wl["normals"], voxel_centered=wl["vc"])
@@ -416,7 +416,8 @@ def main():
     def e2e_step():
       nonlocal d2h
       if world > 1:
-        sm.mesh_slab(hnp, shape[2], zr[0], close=wl["close"], finalize=False)
+        sm.mesh_slab(hnp, shape[2], zr[0], close=wl["close"], finalize=wl["normals"], voxel_centered=wl["vc"],
+                     normals=wl["normals"])
       else:
         mesher.mesh(hnp, close=wl["close"])
       d2h = 0

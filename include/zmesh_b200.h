@@ -98,6 +98,16 @@ uint64_t zm_plane_elems(zm_handle* h);
 int zm_export_plane(zm_handle* h, uint32_t* dst_device);
 int zm_set_foreign_plane(zm_handle* h, const uint32_t* src_device);
 
+/* Normals across slab shards.  The faces of a shard's top cube layer touch vertices owned by the next
+ * shard; their contributions (compute_vertex_normals_from_faces, zmesh/chunk_mesh.hpp:345-384) are
+ * accumulated in a caller-owned device buffer of 3 * zm_plane_elems(h) floats (zm_set_normal_plane, before
+ * the zm_finalize with normals; zeroed by the library), sent to the next shard, added there
+ * (zm_add_normal_plane, after its zm_finalize) and normalised by zm_finish_normals.  On a slab shard
+ * zm_finalize(normals=1) leaves the normals un-normalised until zm_finish_normals is called. */
+int zm_set_normal_plane(zm_handle* h, float* out_device);
+int zm_add_normal_plane(zm_handle* h, const float* src_device);
+int zm_finish_normals(zm_handle* h);
+
 /* Replaces CMesher::ids() (cMesher.hpp:46-54).  The reference's order is unspecified
  * (unordered_map iteration); here ids are ascending.  Labels that produced no triangle are
  * absent, label 0 is never meshed (marching_cubes.hpp:438). */

@@ -20,7 +20,7 @@ def main():
   from zmesh_b200 import Mesher
   from zmesh_b200.sharded import ShardedMesher
   from zmesh_b200.synth import voronoi_device
-  from oracle.oracle import canonical_digest  # test infrastructure: the checker
+  from oracle.oracle import assert_same_mesh, canonical_digest  # test infrastructure: the checker
 
   shape, pitch = (256, 256, 320), 40
   ok = True
@@ -30,7 +30,7 @@ def main():
     slab = voronoi_device((shape[0], shape[1], in_hi - in_lo), pitch, np.uint64, seed=5, order="F",
                           origin=(0, 0, in_lo), full_shape=shape, device=local)
     torch.cuda.synchronize()
-    sm.mesh_slab(slab, shape[2], in_lo, close=close)
+    sm.mesh_slab(slab, shape[2], in_lo, close=close, normals=close)  # (normals on the close=True pass)
     ids = sm.all_ids()
     ref = None
     if rank == 0:
@@ -41,11 +41,17 @@ def main():
       assert ref.ids() == ids, (len(ref.ids()), len(ids))
     bad = 0
     for lbl in ids:
-      got = sm.gather_mesh(lbl, dst=0)
+      got = sm.gather_mesh(lbl, dst=0, normals=close)
       if rank == 0:
-        want = ref.get(lbl)
+        want = ref.get(lbl, normals=close)
         if canonical_digest(got.vertices, got.faces) != canonical_digest(want.vertices, want.faces):
           bad += 1
+        elif close:
+          try:
+            assert_same_mesh(got, want, 1e-5, what=f"label {lbl}")
+          except AssertionError as e:
+            print(e, flush=True)
+            bad += 1
     if rank == 0:
       print(f"close={close}: {len(ids)} labels over {world} ranks, {bad} mismatches", flush=True)
       ok = ok and bad == 0 and len(ids) > 0

@@ -10,7 +10,19 @@ from zmesh_b200.sharded import assemble, offsets_from_directories, slab_planes
 pytestmark = pytest.mark.gpu
 
 
-def run_shards(Mesher, vol, res, close, nshards):
+def _kat_volume():
+  """Slab-boundary known-answer volume: a label that crosses every boundary plane, single
+  voxels sitting on and next to boundary planes, a 2-voxel-thick sheet parallel to the slabs."""
+  v = np.zeros((20, 18, 24), dtype=np.uint32, order="F")
+  v[3:6, 3:6, :] = 5            # column through every slab
+  for z in (5, 6, 7, 11, 12, 13, 17, 18):
+    v[10, 9, z] = 9             # isolated voxels on / next to the cut planes of 2, 3, 4 shards
+    v[12 + (z % 3), 4, z] = 11
+  v[14:19, 10:16, 11:13] = 7    # sheet straddling the middle cut
+  return v
+
+
+def run_shards(Mesher, vol, res, close, nshards, normals=False):
   import torch
   axis = 0 if vol.flags.c_contiguous and not vol.flags.f_contiguous else 2
   order = "C" if axis == 0 else "F"
@@ -34,13 +46,28 @@ def run_shards(Mesher, vol, res, close, nshards):
     ms[r].sync()
     ms[r - 1].set_foreign_plane(t.data_ptr())
     keep.append(t)
+  if normals:
+    # contributions of every shard's top cube layer to the next shard's first-plane vertices
+    nplanes = {}
+    for r, m in enumerate(ms):
+      if r < nshards - 1:
+        nplanes[r] = torch.empty(3 * m.plane_elems(), dtype=torch.float32, device="cuda:0")
+        m.set_normal_plane(nplanes[r].data_ptr())
+      m.finalize(normals=True, voxel_centered=True)
+      m.sync()
+    for r, m in enumerate(ms):
+      if r > 0:
+        m.add_normal_plane(nplanes[r - 1].data_ptr())
+      m.finish_normals()
+    keep.append(nplanes)
   ids = sorted(set(i for m in ms for i in m.ids()))
   out = {}
   for lbl in ids:
     parts = []
     for m in ms:
-      g = m.get(lbl, normals=False, voxel_centered=True)
-      parts.append((g.vertices, g.faces) if len(g.vertices) or len(g.faces) else None)
+      g = m.get(lbl, normals=normals, voxel_centered=True)
+      part = (g.vertices, g.faces, g.normals) if normals else (g.vertices, g.faces)
+      parts.append(part if len(g.vertices) or len(g.faces) else None)
     out[lbl] = assemble(parts)
   return ids, out, keep
 
@@ -51,6 +78,8 @@ CASES = [
   ("random_u32_C_close", lambda: random_volume((30, 20, 33), 40, np.uint32, 7, "C"), (1, 2, 3), True, (2, 3)),
   ("random_u16_F_thin", lambda: random_volume((34, 9, 17), 6, np.uint16, 8, "F"), (1, 1, 1), False, (2, 8)),
   ("tile_aligned_u8_F", lambda: random_volume((64, 16, 33), 5, np.uint8, 9, "F"), (1, 1, 1), False, (2, 4)),
+  ("boundary_kat", _kat_volume, (4, 4, 40), False, (2, 3, 4)),
+  ("boundary_kat_close", _kat_volume, (4, 4, 40), True, (2, 3, 4)),
 ]
 
 
@@ -67,6 +96,26 @@ def test_shards_assemble_to_single_shot(build_all, case):
     assert ids == want_ids, (name, n)
     for lbl in ids:
       assert_same_mesh(meshes[lbl], cpu.get(lbl, normals=False, voxel_centered=True), what=f"{name} n={n} label {lbl}")
+
+
+NORMAL_CASES = [c for c in CASES if c[0] in ("voronoi_u64_F_close", "random_u32_C_close", "boundary_kat", "tile_aligned_u8_F")]
+
+
+@pytest.mark.parametrize("case", NORMAL_CASES, ids=[c[0] for c in NORMAL_CASES])
+def test_shards_normals_match_single_shot(build_all, case):
+  """Normals across shards: the top cube layer's contributions travel to the next shard (tolerance 1e-5
+  absolute on unit vectors, the bar of the single-GPU path: float32 accumulation order differs)."""
+  from zmesh_b200 import Mesher
+  name, make, res, close, shard_counts = case
+  vol = make()
+  cpu = OracleMesher(res, "port")
+  cpu.mesh(vol, close=close)
+  for n in shard_counts[:2]:
+    ids, meshes, _keep = run_shards(Mesher, vol, res, close, n, normals=True)
+    assert ids == sorted(cpu.ids()), (name, n)
+    for lbl in ids:
+      assert meshes[lbl].normals is not None
+      assert_same_mesh(meshes[lbl], cpu.get(lbl, normals=True, voxel_centered=True), 1e-5, what=f"{name} n={n} label {lbl}")
 
 
 def test_slab_requires_exchange(build_all):

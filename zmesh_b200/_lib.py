@@ -74,6 +74,9 @@ SYMBOLS = {
   "zm_plane_elems": (C.c_uint64, [C.c_void_p]),
   "zm_export_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
   "zm_set_foreign_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
+  "zm_set_normal_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
+  "zm_add_normal_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
+  "zm_finish_normals": (C.c_int, [C.c_void_p]),
   "zm_num_ids": (C.c_uint64, [C.c_void_p]),
   "zm_ids": (C.c_int, [C.c_void_p, _u64p, C.c_uint64]),
   "zm_get_counts": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, _u64p]),

@@ -47,6 +47,7 @@ struct LabelRec {
 
 struct FinalState {
   bool faces_valid = false, verts_valid = false, normals_valid = false;
+  bool normals_pending = false;  // slab shard: accumulated, awaiting zm_add_normal_plane / zm_finish_normals
   int voxel_centered = 0, transpose = 0, normals_transpose = 0;
   float off[3] = {0, 0, 0};
 };
@@ -74,6 +75,7 @@ struct zm_handle {
   DevBuf d_voff, d_tmpA, d_tmpB;     // slab sharding: per-table-slot index offsets; upload scratch
   bool tl_fixed = false, have_voff = false, slab_mode = false;
   const uint32_t* foreign = nullptr;  // borrowed: boundary-plane indices received from the next shard
+  float* nplane_out = nullptr;        // borrowed: normal contributions to the next shard's first-plane vertices
   uint64_t capL = 0;
   zm::Control* h_ctl = nullptr;  // pinned
   std::vector<uint64_t> h_list;
@@ -145,7 +147,8 @@ KernelSet kernel_set(int label_bytes, bool c_order) {
 }
 
 pass2_fn emit_kernel(bool c_order, bool normals, bool slab) {
-  if (slab) return c_order ? k_emit<true, false, true> : k_emit<false, false, true>;  // (no normals for slabs yet)
+  if (slab && normals) return c_order ? k_emit<true, true, true> : k_emit<false, true, true>;
+  if (slab) return c_order ? k_emit<true, false, true> : k_emit<false, false, true>;
   if (c_order) return normals ? k_emit<true, true, false> : k_emit<true, false, false>;
   return normals ? k_emit<false, true, false> : k_emit<false, false, false>;
 }
@@ -266,6 +269,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   h->tl_fixed = false;
   h->have_voff = false;
   h->foreign = nullptr;
+  h->nplane_out = nullptr;
   h->slab_mode = slab != nullptr;
   ZM_CUDA(h, cudaSetDevice(h->device));
   h->stats = zm_stats_t{};
@@ -299,6 +303,8 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   if (vp.Ef < 2 || vp.Em < 2 || vp.Es < 2) return ZM_OK;
   vp.ntf = (vp.Ef + TF - 1) / TF; vp.ntm = (vp.Em + TM - 1) / TM; vp.nts = (vp.Es_own + TS - 1) / TS;
   vp.Efp = vp.ntf * TF;
+  if (slab && 4ull * vp.Em * vp.Efp >= (1ull << 32))
+    return fail(h, ZM_ERR_UNSUPPORTED, "slab plane too large for 32-bit boundary-slot indices (Em * Efp >= 2^30)");
   const unsigned long long ntiles = (unsigned long long)vp.ntf * vp.ntm * vp.nts;
   if (ntiles > 0x7FFFFFFFull) return fail(h, ZM_ERR_UNSUPPORTED, "too many tiles for one launch; shard the volume");
   const unsigned long long nvox = (unsigned long long)vp.nf * vp.nm * vp.ns;
@@ -474,6 +480,7 @@ Pass2Args pass2_args(zm_handle* h) {
   a.n_work = h->n_work;
   a.tl = h->d_tl.as<TLEntry>();
   a.foreign = h->foreign;
+  a.fnormals = h->nplane_out;
   return a;
 }
 
@@ -498,8 +505,10 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
   if (h->Vtot && h->n_work) {
     if (h->vp.Es_own < h->vp.Es && !h->foreign)
       return fail(h, ZM_ERR_STATE, "slab shard: zm_set_foreign_plane must be called before the first get/finalize");
-    if (normals && h->slab_mode)
-      return fail(h, ZM_ERR_UNSUPPORTED, "normals are not available for slab shards yet");
+    if (normals && h->slab_mode && f.normals_pending)
+      return fail(h, ZM_ERR_STATE, "slab shard: normals await zm_add_normal_plane / zm_finish_normals");
+    if (need_normals && h->vp.Es_own < h->vp.Es && !h->nplane_out)
+      return fail(h, ZM_ERR_STATE, "slab shard: zm_set_normal_plane must be called before a finalize with normals");
     int rc = ensure_tl_fixed(h);
     if (rc != ZM_OK) return rc;
     ZM_CUDA(h, h->d_faces.ensure((size_t)h->Ttot * 12));
@@ -507,6 +516,8 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     if (need_normals) {
       ZM_CUDA(h, h->d_normals.ensure((size_t)h->Vtot * 12));
       ZM_CUDA(h, cudaMemsetAsync(h->d_normals.p, 0, (size_t)h->Vtot * 12, st));
+      if (h->slab_mode && h->nplane_out)
+        ZM_CUDA(h, cudaMemsetAsync(h->nplane_out, 0, (size_t)zm_plane_elems(h) * 12, st));
     }
     Pass2Args a = pass2_args(h);
     a.faces = h->d_faces.as<uint32_t>();
@@ -530,7 +541,7 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
       ++launches;
     }
     ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
-    if (need_normals) {
+    if (need_normals && !h->slab_mode) {  // (slab shards normalise in zm_finish_normals, after the plane exchange)
       k_normals_normalize<<<grid_for(h->Vtot, 256), 256, 0, st>>>(h->d_normals.as<float>(), h->Vtot);
       ZM_CUDA(h, cudaGetLastError());
       ++launches;
@@ -547,7 +558,15 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
   f.voxel_centered = voxel_centered;
   f.transpose = transpose;
   f.off[0] = o[0]; f.off[1] = o[1]; f.off[2] = o[2];
-  if (need_normals) { f.normals_valid = true; f.normals_transpose = transpose; }
+  if (need_normals) {
+    f.normals_transpose = transpose;
+    if (h->slab_mode) f.normals_pending = true;
+    else f.normals_valid = true;
+  }
+  if (normals && h->slab_mode && !f.normals_valid && !f.normals_pending) {  // (nothing to accumulate on this shard)
+    f.normals_pending = true;
+    f.normals_transpose = transpose;
+  }
   return ZM_OK;
 }
 
@@ -722,6 +741,40 @@ int zm_export_plane(zm_handle* h, uint32_t* dst_device) {
 int zm_set_foreign_plane(zm_handle* h, const uint32_t* src_device) {
   if (!h) return ZM_ERR_INVALID;
   h->foreign = src_device;
+  return ZM_OK;
+}
+
+int zm_set_normal_plane(zm_handle* h, float* out_device) {
+  if (!h) return ZM_ERR_INVALID;
+  h->nplane_out = out_device;
+  return ZM_OK;
+}
+
+int zm_add_normal_plane(zm_handle* h, const float* src_device) {
+  if (!h || !src_device) return ZM_ERR_INVALID;
+  if (!h->has_result || !h->fin.normals_pending) return fail(h, ZM_ERR_STATE, "zm_finalize with normals has not been called on this slab shard");
+  if (!h->n_work || !h->Vtot) return ZM_OK;
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  Pass2Args a = pass2_args(h);
+  a.normals = h->d_normals.as<float>();
+  const uint32_t grid = std::min<uint32_t>((h->n_work + NT_V / 32 - 1) / (NT_V / 32), (uint32_t)h->num_sms * 16u);
+  if (h->c_order) k_import_plane_normals<true><<<grid, NT_V, 0, h->stream>>>(h->vp, a, src_device);
+  else k_import_plane_normals<false><<<grid, NT_V, 0, h->stream>>>(h->vp, a, src_device);
+  ZM_CUDA(h, cudaGetLastError());
+  return ZM_OK;
+}
+
+int zm_finish_normals(zm_handle* h) {
+  if (!h) return ZM_ERR_INVALID;
+  if (!h->has_result || !h->fin.normals_pending) return fail(h, ZM_ERR_STATE, "no pending normals on this handle");
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  if (h->Vtot && h->n_work) {
+    k_normals_normalize<<<grid_for(h->Vtot, 256), 256, 0, h->stream>>>(h->d_normals.as<float>(), h->Vtot);
+    ZM_CUDA(h, cudaGetLastError());
+    ZM_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->fin.normals_pending = false;
+  h->fin.normals_valid = true;
   return ZM_OK;
 }
 

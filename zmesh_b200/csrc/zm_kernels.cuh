@@ -979,6 +979,7 @@ struct Pass2Args {
   int voxel_centered, transpose;
   int write_faces, write_verts;
   const uint32_t* foreign;  // slab sharding: final indices of the top plane's slots, [Em][Efp][4], from the next shard
+  float* fnormals;          // slab sharding + normals: contributions to the next shard's first-plane vertices, [Em][Efp][4][3]
 };
 
 __device__ __forceinline__ float len3(float x, float y, float z) {
@@ -1233,16 +1234,20 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
           const uint32_t tab = s_tab[(uc >> 16) * CASE_TRIS + t];
           const uint32_t voff = SLAB ? rvo[cw][src] : 0u;
           uint32_t vi[3];
+          uint32_t fslot[3];  // (SLAB && NORMALS) boundary-plane slot of a corner owned by the next shard, else ~0
           float p[3][3];
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
+            fslot[c] = 0xFFFFFFFFu;
             const uint32_t en = (tab >> (9 * c)) & 0x1FFu;
             const uint32_t lfx = lf0 + (en >> 8), slot = en & 7u;
             const uint32_t uw = u0 + (en & 0xFFu);  // word of (row, plane) in the first segment
             const uint32_t rr = uw >> 4;
             // slot = 2*axis + side; side 0: the owner (lower) voxel carries the label, 1: the upper one
             if (SLAB && rr - ftop9 < (uint32_t)RM) {
-              vi[c] = __ldg(a.foreign + 4ull * ((size_t)(em0 + rr - ftop9) * vp.Efp + ef0 + lfx) + slot);
+              const uint32_t fs = 4u * ((em0 + rr - ftop9) * vp.Efp + ef0 + lfx) + slot;  // (zm_mesh_slab rejects planes of 2^32 or more slots)
+              vi[c] = __ldg(a.foreign + fs);
+              if (NORMALS) fslot[c] = fs;
             } else {
               const uint32_t idx = uw + ((lfx >> 5) << 3);
               const uint32_t g = rb[idx] + __popc(Rc[idx] & ((1u << (lfx & 31u)) - 1u));
@@ -1262,6 +1267,11 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
             float* d0 = nb + 3ull * (vi[0] - voff);
             float* d1 = nb + 3ull * (vi[1] - voff);
             float* d2 = nb + 3ull * (vi[2] - voff);
+            if (SLAB) {  // vertices of the next shard: accumulate in the plane buffer that is sent to it
+              if (fslot[0] != 0xFFFFFFFFu) d0 = a.fnormals + 3ull * fslot[0];
+              if (fslot[1] != 0xFFFFFFFFu) d1 = a.fnormals + 3ull * fslot[1];
+              if (fslot[2] != 0xFFFFFFFFu) d2 = a.fnormals + 3ull * fslot[2];
+            }
             // legacy faces (t0,t2,t1) = the stored row reversed
             if (a.transpose) face_normal_scatter(p[2], p[1], p[0], d2, d1, d0);
             else face_normal_scatter(p[0], p[1], p[2], d0, d1, d2);
@@ -1314,6 +1324,32 @@ __global__ void __launch_bounds__(NT_V) k_export_plane(const VolParams vp, const
       if ((vidx >> 8) != 0u || s6 >= 4u) continue;
       const uint32_t ef = tf * TF + (vidx & 31u), em = tm * TM + ((vidx >> 5) & 7u);
       dst[4ull * ((size_t)em * vp.Efp + ef) + s6] = (uint32_t)(tl[ci].a >> 32) + __ldg(a.perm + h.gbase + i);
+    }
+  }
+}
+
+// slab sharding + normals: add the contributions the shard below accumulated for this shard's first-plane
+// vertices (src[(em * Efp + ef) * 4 + slot][3], same indexing as k_export_plane); every vertex is touched once.
+template <bool CO>
+__global__ void __launch_bounds__(NT_V) k_import_plane_normals(const VolParams vp, const Pass2Args a, const float* src) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t nwarps = gridDim.x * (NT_V / 32);
+  const uint32_t plane_tiles = vp.ntf * vp.ntm;
+  for (uint32_t w = blockIdx.x * (NT_V / 32) + (threadIdx.x >> 5); w < a.n_work; w += nwarps) {
+    const TileHdr h = load_hdr(a.hdr + w);
+    if (h.tile >= plane_tiles || h.nslots == 0) continue;
+    const uint32_t tf = h.tile % vp.ntf, tm = h.tile / vp.ntf;
+    const TLEntry* tl = a.tl + h.tlbase;
+    for (uint32_t i = lane; i < h.nslots; i += 32) {
+      const uint32_t v = __ldg(a.vinfo + h.gbase + i);
+      const uint32_t vidx = v & 0x7FFu, s6 = (v >> 11) & 7u, ci = v >> 14;
+      if ((vidx >> 8) != 0u || s6 >= 4u) continue;
+      const uint32_t ef = tf * TF + (vidx & 31u), em = tm * TM + ((vidx >> 5) & 7u);
+      const float* in = src + 3ull * (4ull * ((size_t)em * vp.Efp + ef) + s6);
+      float* nn = a.normals + 3ull * ((tl[ci].a & 0xFFFFFFFFull) + __ldg(a.perm + h.gbase + i));
+      nn[0] = __fadd_rn(nn[0], in[0]);
+      nn[1] = __fadd_rn(nn[1], in[1]);
+      nn[2] = __fadd_rn(nn[2], in[2]);
     }
   }
 }

@@ -198,6 +198,16 @@ class Mesher:
   def set_foreign_plane(self, src_device_ptr):
     self._check(self._lib.zm_set_foreign_plane(self._h, C.c_void_p(int(src_device_ptr)) if src_device_ptr else None))
 
+  def set_normal_plane(self, dst_device_ptr):
+    """Device buffer (3 * plane_elems() float32) for the normal contributions to the next shard's vertices."""
+    self._check(self._lib.zm_set_normal_plane(self._h, C.c_void_p(int(dst_device_ptr)) if dst_device_ptr else None))
+
+  def add_normal_plane(self, src_device_ptr: int):
+    self._check(self._lib.zm_add_normal_plane(self._h, C.c_void_p(int(src_device_ptr))))
+
+  def finish_normals(self):
+    self._check(self._lib.zm_finish_normals(self._h))
+
   def set_stream(self, cuda_stream):
     """Queue all work on a caller-owned CUDA stream (integer cudaStream_t); None restores the own one."""
     self._check(self._lib.zm_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None))

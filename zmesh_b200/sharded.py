@@ -14,6 +14,10 @@ CONCATENATE, there is nothing to dedup.  What has to be exchanged is only bookke
      (uint32 [Em][Efp][4], one NCCL send/recv between neighbours), which rank r's face kernel
      reads for the corners of its top cube layer.
 
+  3. with normals: the faces of rank r's top cube layer touch vertices owned by rank r+1; their
+     contributions are accumulated in a plane-shaped buffer (float32 [Em][Efp][4][3]), sent to rank r+1
+     (one more neighbour send/recv), added there, and only then are the normals normalised.
+
 The result stays distributed: rank r holds, for every label, the vertices it owns and the faces of
 its cubes with global (cross-rank) indices; `gather_mesh(label)` concatenates the parts in rank
 order, which is bit-identical (as canonical sets) to the single-GPU mesh.
@@ -99,12 +103,14 @@ def all_gather_directories(labels, nv, group=None, device=None):
 
 
 def assemble(parts):
-  """Concatenate per-rank parts [(vertices, faces) or None, ...] in rank order -> Mesh."""
+  """Concatenate per-rank parts [(vertices, faces[, normals]) or None, ...] in rank order -> Mesh."""
   vs = [p[0] for p in parts if p is not None and len(p[0])]
   fs = [p[1] for p in parts if p is not None and len(p[1])]
+  ns = [p[2] for p in parts if p is not None and len(p) > 2 and p[2] is not None and len(p[2])]
   v = np.concatenate(vs) if vs else np.zeros((0, 3), np.float32)
   f = np.concatenate(fs) if fs else np.zeros((0, 3), np.uint32)
-  return Mesh(v, f, None)
+  n = np.concatenate(ns) if ns and sum(len(x) for x in ns) == len(v) else None
+  return Mesh(v, f, n)
 
 
 class ShardedMesher:
@@ -120,13 +126,15 @@ class ShardedMesher:
     self.mesher = Mesher(voxel_res, device=self.device)
     self._plane_send = None
     self._plane_recv = None
+    self._nplane_out = None
+    self._nplane_in = None
     self._dir = None
 
   def planes(self, full_extent: int, close: bool = False):
     return slab_planes(int(full_extent), bool(close), self.rank, self.world)
 
   def mesh_slab(self, data, full_extent: int, buf_lo: int, close: bool = False, finalize: bool = True,
-                voxel_centered: bool = False):
+                voxel_centered: bool = False, normals: bool = False):
     """data: this rank's planes [buf_lo, buf_lo + n) of the volume along the slab axis (numpy array or
     CUDA tensor), covering at least planes(full_extent, close)[2:4]."""
     import torch
@@ -169,9 +177,31 @@ class ShardedMesher:
     m.set_foreign_plane(self._plane_recv.data_ptr() if not last else None)
     tm("plane_exchange")
     out = None
-    if finalize:
-      out = m.finalize(normals=False, voxel_centered=voxel_centered)
+    if finalize or normals:
+      if normals and not last:
+        if self._nplane_out is None or self._nplane_out.numel() != 3 * n:
+          self._nplane_out = torch.empty(3 * n, dtype=torch.float32, device=dev)
+        m.set_normal_plane(self._nplane_out.data_ptr())
+      out = m.finalize(normals=normals, voxel_centered=voxel_centered)
       tm("pass2")
+      if normals:
+        # normal contributions of the top cube layer to the next shard's first-plane vertices: rank r -> r+1
+        ops = []
+        if not last:
+          ops.append(dist.P2POp(dist.isend, self._nplane_out, self.rank + 1, group=self.group))
+        if self.rank > 0:
+          if self._nplane_in is None or self._nplane_in.numel() != 3 * n:
+            self._nplane_in = torch.empty(3 * n, dtype=torch.float32, device=dev)
+          ops.append(dist.P2POp(dist.irecv, self._nplane_in, self.rank - 1, group=self.group))
+        if ops:
+          for w in dist.batch_isend_irecv(ops):
+            w.wait()
+          if not same_stream:
+            stream.synchronize()
+        if self.rank > 0:
+          m.add_normal_plane(self._nplane_in.data_ptr())
+        m.finish_normals()
+        tm("normal_exchange")
     return out
 
   def _timer(self):
@@ -192,12 +222,12 @@ class ShardedMesher:
       t[0] = now
     return mark
 
-  def local_part(self, label, voxel_centered: bool = False):
-    """(vertices, faces) this rank holds for `label` (faces carry cross-rank indices) or None."""
-    mesh = self.mesher.get(label, normals=False, voxel_centered=voxel_centered)
+  def local_part(self, label, voxel_centered: bool = False, normals: bool = False):
+    """(vertices, faces[, normals]) this rank holds for `label` (faces carry cross-rank indices) or None."""
+    mesh = self.mesher.get(label, normals=normals, voxel_centered=voxel_centered)
     if len(mesh.vertices) == 0 and len(mesh.faces) == 0:
       return None
-    return mesh.vertices, mesh.faces
+    return (mesh.vertices, mesh.faces, mesh.normals) if normals else (mesh.vertices, mesh.faces)
 
   def all_ids(self):
     """Sorted ids of the whole volume (every rank gets the same list)."""
@@ -207,10 +237,10 @@ class ShardedMesher:
     dist.all_gather_object(outs, mine, group=self.group)
     return sorted(set(i for o in outs for i in o))
 
-  def gather_mesh(self, label, dst: int = 0, voxel_centered: bool = False):
+  def gather_mesh(self, label, dst: int = 0, voxel_centered: bool = False, normals: bool = False):
     """Assemble the full mesh of `label` on rank `dst` (None elsewhere)."""
     import torch.distributed as dist
-    part = self.local_part(label, voxel_centered)
+    part = self.local_part(label, voxel_centered, normals)
     outs = [None] * self.world if self.rank == dst else None
     dist.gather_object(part, outs, dst=dst, group=self.group)
     if self.rank != dst:
