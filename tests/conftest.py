@@ -23,6 +23,13 @@ def connectomics():
 
 
 @pytest.fixture(scope="session")
+def fanc():
+  """The reference's C-vs-F regression volume (fanc_bug.npy.gz, automated_test.py:17-20): bool (512, 512, 128, 1)."""
+  with gzip.open(os.path.join(GOLDEN, "fanc_bug.npy.gz"), "rb") as f:
+    return np.load(f)
+
+
+@pytest.fixture(scope="session")
 def ref_cases():
   return np.load(os.path.join(GOLDEN, "ref_cases.npz"))
 

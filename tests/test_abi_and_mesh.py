@@ -84,3 +84,52 @@ def test_mesh_codecs_roundtrip():
   assert Mesh.from_precomputed(with_normals.to_precomputed()) != with_normals  # normals are not stored
   with pytest.raises(ValueError):
     Mesh.from_precomputed(m.to_precomputed()[:20])
+
+
+def _reference_volume(data):
+  """What the reference hands its C++ mesher for a contiguous array: `reshape(data, (data.size,))`
+  (zmesh/_zmesh.pyx:698-729, Fortran order tested first) and the extents data.shape[:3] with
+  c_order = data.flags.c_contiguous (:970-976) -- restated here with plain indexing."""
+  flat = data.ravel(order="F" if data.flags.f_contiguous else "C")
+  sx, sy, sz = data.shape[:3]
+  order = "C" if data.flags.c_contiguous else "F"
+  return flat[: sx * sy * sz].reshape((sx, sy, sz), order=order)
+
+
+def test_as_volume3d_follows_the_reference():
+  from zmesh_b200.mesher import as_volume3d
+  rng = np.random.default_rng(0)
+  base = rng.integers(0, 5, size=(6, 5, 4), dtype=np.uint16)
+  for arr in (np.ascontiguousarray(base), np.asfortranarray(base)):
+    out = as_volume3d(arr)
+    assert out is arr  # used in place
+    for four_d in (arr[..., None], arr[..., None, None]):
+      out = as_volume3d(four_d)
+      assert out.shape == (6, 5, 4) and np.shares_memory(out, arr) and np.array_equal(out, base)
+      assert out.flags.c_contiguous == arr.flags.c_contiguous
+      assert np.array_equal(as_volume3d(four_d, close=True), base)
+  strided = np.ascontiguousarray(rng.integers(0, 5, size=(12, 5, 12), dtype=np.uint8))[::2, :, ::3]
+  out = as_volume3d(strided)
+  assert out.flags.c_contiguous and np.array_equal(out, strided)
+  # extra axes with extent > 1 (automated_test.py:195-213, transpose=True): the first sx*sy*sz elements of the buffer
+  wide = rng.integers(0, 5, size=(7, 6, 5, 3), dtype=np.uint32)
+  for arr in (wide, np.asfortranarray(wide), wide.T, np.ascontiguousarray(wide.T)):
+    out = as_volume3d(arr)
+    assert out.shape == arr.shape[:3] and np.shares_memory(out, arr)
+    assert np.array_equal(out, _reference_volume(arr))
+    with pytest.raises(ValueError):
+      as_volume3d(arr, close=True)
+  with pytest.raises(IndexError):
+    as_volume3d(np.zeros((4, 4), dtype=np.uint8))
+
+
+def test_fanc_fixture_shape():
+  """The reference's C-vs-F regression volume (fanc_bug.npy.gz): 4-d boolean, meshed as 3-d."""
+  import gzip
+  from tests.conftest import GOLDEN
+  from zmesh_b200.mesher import as_volume3d
+  with gzip.open(os.path.join(GOLDEN, "fanc_bug.npy.gz"), "rb") as f:
+    v = np.load(f)
+  assert v.shape == (512, 512, 128, 1) and v.dtype == np.bool_
+  assert as_volume3d(v).shape == (512, 512, 128)
+  assert as_volume3d(v.T).shape == (1, 128, 512)  # no cube along x: the reference finds no ids

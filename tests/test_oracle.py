@@ -90,3 +90,23 @@ def test_port_matches_reference_shim(order, close, connectomics):
         assert_same_mesh(a.get(lbl, normals=True, voxel_centered=vc), b.get(lbl, normals=True, voxel_centered=vc),
                          what=f"{lbl}")
       assert_same_mesh(a.get_mesh(lbl, normals=True), b.get_mesh(lbl, normals=True), what=f"legacy {lbl}")
+
+
+@pytest.mark.parametrize("kind", ["port", "reference"])
+def test_fanc_bug_c_and_f_order(kind, fanc):
+  """automated_test.py:195-213 (the C-vs-F regression volume) on the oracle, strengthened to canonical
+  equality of the two orders; the port and the compiled reference must agree on the result."""
+  if kind == "reference" and not have_reference():
+    pytest.skip("oracle/_ref/libzmesh_ref.so not built here")
+  vol = fanc[..., 0]
+  f, c = OracleMesher((1, 1, 1), kind), OracleMesher((1, 1, 1), kind)
+  f.mesh(np.asfortranarray(vol))
+  c.mesh(np.ascontiguousarray(vol))
+  assert sorted(f.ids()) == sorted(c.ids()) == [1]
+  a, b = f.get(1), c.get(1)
+  assert_same_mesh(a, b, what="fanc C vs F")
+  assert np.isclose(a.vertices.mean(), b.vertices.mean())
+  if kind == "reference":
+    p = OracleMesher((1, 1, 1), "port")
+    p.mesh(np.ascontiguousarray(vol))
+    assert_same_mesh(p.get(1), b, what="fanc port vs reference")

@@ -213,6 +213,24 @@ def test_c_and_f_order_give_identical_sets(Mesher, connectomics):
     assert_same_mesh(f.get_mesh(lbl), c.get_mesh(lbl), what=f"legacy {lbl}")
 
 
+@pytest.mark.parametrize("transpose", [True, False])
+def test_fanc_bug(Mesher, fanc, transpose):
+  """automated_test.py:195-213 run against the drop-in (4-d boolean input; transposed it has extent 1 along x
+  and the reference finds nothing), strengthened to canonical equality and checked against the oracle."""
+  lab = fanc.T if transpose else fanc
+  f, c = Mesher((1, 1, 1)), Mesher((1, 1, 1))
+  f.mesh(np.asfortranarray(lab))
+  c.mesh(np.ascontiguousarray(lab))
+  assert c.ids() == f.ids() == ([] if transpose else [1])
+  for label in c.ids():
+    cm, fm = c.get(label, normals=False, reduction_factor=0), f.get(label, normals=False, reduction_factor=0)
+    assert np.isclose(cm.vertices.mean(), fm.vertices.mean())
+    assert_same_mesh(cm, fm, what="fanc C vs F")
+    cpu = OracleMesher((1, 1, 1), "port")
+    cpu.mesh(np.ascontiguousarray(lab[..., 0]))
+    assert_same_mesh(cm, cpu.get(label), what="fanc vs oracle")
+
+
 def test_degenerate_volumes_512(Mesher):
   """BASELINE config 2: all-zero and single-label 512^3 uint32."""
   m = Mesher((4, 4, 40))

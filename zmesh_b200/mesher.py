@@ -35,6 +35,33 @@ def _f3(a):
   return a
 
 
+def as_volume3d(data: np.ndarray, close: bool = False) -> np.ndarray:
+  """The (sx, sy, sz) array the reference meshes for `data`, sharing memory with it where the reference
+  does (zmesh/_zmesh.pyx:499-506 and the typed wrappers, e.g. :970-976):
+
+    * fewer than three axes: IndexError (the reference indexes data.shape[2]);
+    * neither C- nor Fortran-contiguous: copied to C order (:499-500);
+    * more than three axes: the reference flattens the buffer in its memory order and hands C++ the extents
+      shape[:3], i.e. it meshes the FIRST sx*sy*sz elements of the buffer laid out as (sx, sy, sz) in that
+      order.  For trailing axes of extent 1 this is the array without them; in general it is what
+      test_fanc_bug[transpose=True] exercises (automated_test.py:195-213: shape (1, 128, 512, 512)).
+      With close=True the reference's padded copy broadcasts over the extra axes and then meshes a
+      prefix of THAT buffer, which is not meaningful: only extra axes of extent 1 are accepted here.
+  """
+  if data.ndim < 3:
+    raise IndexError("tuple index out of range")
+  if not data.flags.c_contiguous and not data.flags.f_contiguous:
+    data = np.ascontiguousarray(data)
+  if data.ndim == 3:
+    return data
+  shape = tuple(int(s) for s in data.shape[:3])
+  n3 = shape[0] * shape[1] * shape[2]
+  if close and int(data.size) != n3:
+    raise ValueError("close=True needs a 3d volume (extra axes must have extent 1)")
+  order = "C" if data.flags.c_contiguous else "F"
+  return data.reshape(-1, order=order)[:n3].reshape(shape, order=order)
+
+
 class _PinnedBlock:
   """Page-locked host block the bulk device-to-host copy lands in; arrays handed to the user are views
   of it and keep it alive (the ctypes buffer they are based on references the block)."""
@@ -138,19 +165,11 @@ class Mesher:
       return self._mesh_device(data, cai, bool(close))
 
     data = np.asarray(data) if not isinstance(data, np.ndarray) else data
-    if data.ndim < 3:
-      raise IndexError("tuple index out of range")  # the reference indexes data.shape[2]
     nbytes = data.dtype.itemsize
     if nbytes not in (1, 2, 4, 8):
       raise TypeError(f"unsupported label dtype {data.dtype}")
-    shape = tuple(int(s) for s in data.shape[:3])
-    if int(np.prod(data.shape, dtype=np.int64)) != shape[0] * shape[1] * shape[2]:
-      raise ValueError("only the first three axes may have extent > 1")
-    if data.ndim > 3:
-      data = data.reshape(shape, order="C" if data.flags.c_contiguous else "F") \
-        if (data.flags.c_contiguous or data.flags.f_contiguous) else data.reshape(shape)
-    if not data.flags.c_contiguous and not data.flags.f_contiguous:
-      data = np.ascontiguousarray(data)
+    data = as_volume3d(data, bool(close))
+    shape = tuple(int(s) for s in data.shape)
     c_order = 1 if data.flags.c_contiguous else 0
     self._max_label = (1 << (8 * nbytes)) - 1
     self._check(self._call_mesh(data.ctypes.data, nbytes, shape, c_order, close, 0))
