@@ -342,3 +342,71 @@ def test_device_generator_matches_numpy(Mesher, order, dtype):
   assert gpu.ids() == sorted(cpu.ids())
   for lbl in gpu.ids()[:20]:
     assert_same_mesh(gpu.get(lbl), cpu.get(lbl), what=str(lbl))
+
+
+def test_config4_full_size_properties(Mesher):
+  """BASELINE config 4 at its full size (Voronoi 1024^3 uint64, pitch 64, close=True, normals, voxel_centered) --
+  far beyond what the oracle finishes in seconds -- through size-independent properties, all labels:
+  the per-label vertex census (V_label = axis-adjacent voxel pairs, the virtual zero border included, with
+  exactly one endpoint == label; computed independently with torch on the device), index integrity of every
+  label's faces, coordinate range under close + voxel_centered, unit normals."""
+  import torch
+  from zmesh_b200.synth import voronoi_device
+  n, pitch, res = 1024, 64, (4.0, 4.0, 40.0)
+  t = voronoi_device((n, n, n), pitch, np.uint64, seed=0, order="F")
+  m = Mesher(res)
+  m.mesh(t, close=True)
+  ids = m.ids()
+  assert len(ids) == (n // pitch) ** 3
+  bulk = m.finalize(normals=True, voxel_centered=True)
+
+  # ---- census on the device (labels as signed bit patterns; every Voronoi label is non-zero) ----
+  tc = t.permute(2, 1, 0)  # the contiguous view (z, y, x); the census is symmetric in the axes
+  assert tc.is_contiguous()
+  keys = np.sort(np.array(ids, dtype=np.uint64).view(np.int64))
+  dkeys = torch.from_numpy(keys).cuda()
+  want = torch.zeros(len(keys), dtype=torch.int64, device="cuda")
+
+  def count(x):
+    want.add_(torch.bincount(torch.searchsorted(dkeys, x.reshape(-1)), minlength=len(keys)))
+
+  def pairs(a, b):
+    d = a != b
+    count(a[d])
+    count(b[d])
+
+  step = 32
+  for z0 in range(0, n, step):
+    z1 = min(n, z0 + step)
+    blk = tc[z0:z1]
+    for ax in (1, 2):
+      pairs(blk.narrow(ax, 0, n - 1), blk.narrow(ax, 1, n - 1))
+      count(blk.select(ax, 0))      # faces on the closed border: the outside voxel is 0
+      count(blk.select(ax, n - 1))
+    hi = min(n, z1 + 1)
+    pairs(tc[z0:hi - 1], tc[z0 + 1:hi])
+  count(tc[0])
+  count(tc[n - 1])
+  want = want.cpu().numpy()
+  del tc, t
+  torch.cuda.empty_cache()
+
+  labels = bulk["labels"].view(np.int64)
+  nv = np.diff(bulk["voff"]).astype(np.int64)
+  nf = np.diff(bulk["foff"]).astype(np.int64)
+  pos = np.searchsorted(keys, labels)
+  assert np.array_equal(keys[pos], labels)
+  assert np.array_equal(nv, want[pos]), "per-label vertex census"
+  assert int(nv.sum()) == bulk["n_vertices"] and int(nf.sum()) == bulk["n_faces"]
+  assert (nf > 0).all()
+
+  v, f, nrm = m.fetch_all(normals=True)
+  lo = np.array(res, dtype=np.float32)          # key 1 under close + voxel_centered: (res * 1 + res) / 2
+  hi = lo * np.float32(n + 1)                   # key 2n + 1
+  assert np.isfinite(v).all() and (v.min(axis=0) == lo).all() and (v.max(axis=0) == hi).all()
+  length = np.sqrt((nrm.astype(np.float64) ** 2).sum(axis=1))
+  ok = ~np.isnan(length)
+  assert ok.mean() > 0.999 and np.abs(length[ok] - 1.0).max() < 1e-5
+  for i in range(0, len(labels), 41):
+    ff = f[bulk["foff"][i]:bulk["foff"][i + 1]]
+    assert int(ff.max()) == nv[i] - 1 and len(np.unique(ff)) == nv[i], int(labels[i])
