@@ -45,6 +45,8 @@ WORKLOADS = {
   "c5": dict(kind="voronoi", shape=(2048, 2048, 2048), dtype="uint64", order="F", res=(4, 4, 40), close=False, normals=False, vc=False, pitch=128),
   # reduced-size stand-ins for development (never the default)
   "c5s": dict(kind="voronoi", shape=(512, 512, 512), dtype="uint64", order="F", res=(4, 4, 40), close=False, normals=False, vc=False, pitch=128),
+  # all-zero volume of c5's size, filled on the device: every tile takes the uniform-region exit (cost floor of pass 1)
+  "c5z": dict(kind="zeros_device", shape=(2048, 2048, 2048), dtype="uint64", order="F", res=(4, 4, 40), close=False, normals=False, vc=False),
 }
 
 
@@ -135,6 +137,9 @@ def device_volume(name, wl, device, zrange=None):
   if wl["kind"] == "voronoi":
     return voronoi_device((shape[0], shape[1], z1 - z0), wl["pitch"], np.dtype(wl["dtype"]), seed=0, order=wl["order"],
                           origin=(0, 0, z0), full_shape=shape, device=device)
+  if wl["kind"] == "zeros_device":
+    tdt = {1: torch.uint8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[np.dtype(wl["dtype"]).itemsize]
+    return torch.zeros((z1 - z0, shape[1], shape[0]), dtype=tdt, device=f"cuda:{device}").permute(2, 1, 0)
   v = host_volume(name, wl, zrange if zrange is not None else None)
   nb = v.dtype.itemsize
   sdt = {1: np.uint8, 2: np.int16, 4: np.int32, 8: np.int64}[nb]

@@ -48,6 +48,10 @@ typedef unsigned long long u64;
 __device__ uint8_t TRI_COUNT_D[256];
 __device__ u64 TRI_NIBBLES_D[256];
 
+#ifndef ZM_S1_ROWMASK
+#define ZM_S1_ROWMASK 1  // 1: row-mask formulation of pass 1's S1 (edge_rows); 0: marching scan (scan_tile)
+#endif
+
 constexpr int TF = 32;  // tile extent along the memory-fastest axis (= one warp per row)
 constexpr int TM = 8;
 constexpr int TS = 8;
@@ -291,7 +295,7 @@ struct __align__(128) P1Smem {
   uint32_t lcnt[Caps<MODE>::LT];   // low 16: vertices of the label in this tile, high 16: triangles
   // per tile-local slot.  MODE 0: local rank (11 bits) | table slot << 11 (7 bits) | voxel-in-tile << 18 | slot << 29;
   // MODE 1: local rank << 12 | table slot, voxel-in-tile | slot << 11 in pstage
-  uint32_t vstage[Caps<MODE>::VCAP];
+  alignas(16) uint32_t vstage[Caps<MODE>::VCAP];  // (ZM_S1_ROWMASK: holds the row masks of edge_rows until S3)
   uint32_t rstage[Caps<MODE>::RCAP];  // voxel-in-tile | case << 11 | table slot << 19
   uint32_t tc[4];                  // tile coordinates (tf, tm, ts)
   uint32_t wtot[NW];               // per s-plane: slots | active voxels << 16
@@ -464,6 +468,49 @@ __device__ __forceinline__ bool scan_tile(const VolParams& vp, P1Smem<L, MODE>& 
   return any;
 }
 
+// S1, row-mask formulation (ZM_S1_ROWMASK): phase A turns every staged row (all RS * RM of them, the halo
+// rows included) into five 32-bit masks with ONE pass of three label compares per voxel --
+//   Ef: voxel != its +f neighbour,  Em: != +m neighbour,  Es: != +s neighbour,  Z: voxel != 0,  Zf: +f neighbour != 0
+// -- and everything per cube / per slot is then bit arithmetic on whole rows (phase B, in tile_body): a cube is
+// uniform iff the 7 edges of a spanning tree of its corners are (4 f-edges, the m-edges at f of the two planes, the
+// s-edge at (f, m)).  The masks live in vstage, which is dead until S3.
+constexpr int EM_WORDS = 8;  // words per staged row in the mask array (5 used)
+template <typename L, int MODE>
+__device__ __forceinline__ void edge_rows(P1Smem<L, MODE>& S, const L* lab) {
+  constexpr int RFP = P1Smem<L, MODE>::RFP;
+  constexpr uint32_t FULL = 0xffffffffu;
+  static_assert(Caps<MODE>::VCAP >= RS * RM * EM_WORDS, "edge masks overlay vstage");
+  static_assert(NW == TM, "warp w marches over s along the rows m = w");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* const em = S.vstage;
+  {  // rows m = warp (< TM, so row m + 1 is staged), s = 0 .. RS-1: the +s neighbour is the next step's own voxel
+    const L* p = lab + warp * RFP + lane;
+    uint32_t* e = em + warp * EM_WORDS;
+    L a = p[0];
+#pragma unroll
+    for (int ls = 0; ls < RS; ++ls) {
+      const L af = p[1], am = p[RFP];
+      const L as_ = ls < RS - 1 ? p[RM * RFP] : a;  // (no plane above the halo plane: Es unused there)
+      const uint32_t ef = __ballot_sync(FULL, a != af), emm = __ballot_sync(FULL, a != am), es = __ballot_sync(FULL, a != as_);
+      const uint32_t z = __ballot_sync(FULL, a != 0), zf = __ballot_sync(FULL, af != 0);
+      if (lane == 0) {
+        *reinterpret_cast<uint4*>(e) = make_uint4(ef, emm, es, z);
+        e[4] = zf;
+      }
+      a = as_;
+      p += RM * RFP;
+      e += RM * EM_WORDS;
+    }
+  }
+  // halo rows m = TM (only ever the "+m" row of a cube: Ef and Z are all that is read): s = warp, and s = TS for warp 0
+  for (int ls = warp; ls < RS; ls += NW) {
+    const L* p = lab + (ls * RM + TM) * RFP + lane;
+    const L a = p[0], af = p[1];
+    const uint32_t ef = __ballot_sync(FULL, a != af), z = __ballot_sync(FULL, a != 0);
+    if (lane == 0) *reinterpret_cast<uint4*>(em + (ls * RM + TM) * EM_WORDS) = make_uint4(ef, 0u, 0u, z);
+  }
+}
+
 enum : int { TILE_EMPTY = 0, TILE_DEFERRED = 1, TILE_DONE = 2 };
 
 // Everything after staging for planes [h0, h0 + nh) of a tile (all 8 in MODE 0).  The caller has
@@ -483,6 +530,51 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
   for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
   if (tid == 0) { S.nrec = 0; S.overflow = 0; S.ci = 0; S.ttot = 0; }
 
+#if ZM_S1_ROWMASK
+  // ---- S1 (row masks): phase A: edge / non-zero masks of all staged rows; phase B: lane j < TM of warp w turns
+  //      them into the bit planes and the active-cube mask of row (w, j), then S2's in-row prefixes ----
+  edge_rows<L, MODE>(S, lab);
+  __syncthreads();
+  bool any = false;
+  uint32_t packed = 0;  // slots of the row | active voxels of the row << 16   (lane j < TM: row j of the plane)
+  if (lane < TM) {
+    const int row = warp * TM + lane;
+    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0, act = 0;
+    if (warp >= h0 && warp < h0 + nh) {
+      const uint32_t* e0 = S.vstage + (warp * RM + lane) * EM_WORDS;
+      const uint4 q = *reinterpret_cast<const uint4*>(e0);                     // Ef, Em, Es, Z of (m, s)
+      const uint32_t zf = e0[4];
+      const uint4 qm = *reinterpret_cast<const uint4*>(e0 + EM_WORDS);         // (m + 1, s)
+      const uint4 qs = *reinterpret_cast<const uint4*>(e0 + RM * EM_WORDS);    // (m, s + 1)
+      const uint32_t ef3 = e0[(RM + 1) * EM_WORDS];                            // Ef of (m + 1, s + 1)
+      const uint32_t nonuni = q.x | qm.x | qs.x | ef3 | q.y | qs.y | q.z;     // cube has two different corners
+      uint32_t pf = q.x, pm = q.y, ps = q.z, cube = nonuni;
+      if (!(ef0 + TF + 1 <= vp.Ef && em0 + TM + 1 <= vp.Em && es0 + TS + 1 <= vp.Es)) {
+        // volume boundary within reach: slots exist only on edges whose upper voxel is inside the (extended)
+        // volume and whose lower voxel this shard owns; a cube needs all three upper neighbours
+        const uint32_t nfv = vp.Ef - ef0;  // valid columns from ef0 (>= 1)
+        const uint32_t VF = nfv >= 32u ? FULL : (1u << nfv) - 1u;          // ef < Ef
+        const uint32_t NF1 = nfv >= 33u ? FULL : (1u << (nfv - 1u)) - 1u;  // ef + 1 < Ef
+        const uint32_t em_ = em0 + (uint32_t)lane, es_ = es0 + (uint32_t)warp;
+        const bool rowok = em_ < vp.Em && es_ < vp.Es_own;
+        const bool nm1 = em_ + 1 < vp.Em, ns1 = es_ + 1 < vp.Es;
+        pf = rowok ? pf & NF1 : 0u;
+        pm = rowok && nm1 ? pm & VF : 0u;
+        ps = rowok && ns1 ? ps & VF : 0u;
+        cube = rowok && nm1 && ns1 ? nonuni & NF1 : 0u;
+      }
+      b0 = pf & q.w; b1 = pf & zf; b2 = pm & q.w; b3 = pm & qm.w; b4 = ps & q.w; b5 = ps & qs.w;
+      act = b0 | b1 | b2 | b3 | b4 | b5 | cube;  // (interior tiles: an edge with different labels makes the cube non-uniform)
+    }
+    *reinterpret_cast<uint4*>(&S.pl[row][0]) = make_uint4(b0, b1, b2, b3);
+    *reinterpret_cast<uint4*>(&S.pl[row][4]) = make_uint4(b4, b5, 0u, act);
+    any = act != 0u;
+    const uint32_t c0 = __popc(b0), c1 = c0 + __popc(b1), c2 = c1 + __popc(b2), c3 = c2 + __popc(b3);
+    const uint32_t c4 = c3 + __popc(b4);
+    *reinterpret_cast<uint2*>(S.pp8[row]) = make_uint2((c0 << 8) | (c1 << 16) | (c2 << 24), c3 | (c4 << 8));
+    packed = (c4 + __popc(b5)) | ((uint32_t)__popc(act) << 16);
+  }
+#else
   // ---- S1: slot masks -> bit planes, active-cube masks ----
   bool any = false;
   if (warp >= h0 && warp < h0 + nh) {
@@ -507,6 +599,7 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     *reinterpret_cast<uint2*>(S.pp8[row]) = make_uint2((c0 << 8) | (c1 << 16) | (c2 << 24), c3 | (c4 << 8));
     packed = (c4 + __popc(q1.y)) | ((uint32_t)__popc(q1.w) << 16);
   }
+#endif
   uint32_t rinc = packed;
 #pragma unroll
   for (int d = 1; d < TM; d <<= 1) {
