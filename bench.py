@@ -472,7 +472,8 @@ def main():
         "sharding": (f"z-slabs with 1-plane halo over {world} ranks; vertices owned by voxel (exactly once across "
                      "ranks), face indices made global by an all-gather of per-label counts + a neighbour "
                      "send/recv of the boundary plane (NCCL); results stay distributed") if world > 1 else "single GPU",
-        "labels": int(st["n_labels"]), "vertices": int(totV), "faces": int(totT)}),
+        "labels": int(st["n_labels"]), "vertices": int(totV), "faces": int(totT),
+        "tiles": {"all": int(st["n_tiles"]), "non_empty": int(st["n_active_tiles"]), "dense_redo": int(st["n_dense_tiles"])}}),
       "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
       "clocks": clocks.summary(),
     }

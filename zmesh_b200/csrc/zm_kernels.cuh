@@ -52,6 +52,14 @@ __device__ u64 TRI_NIBBLES_D[256];
 #define ZM_S1_ROWMASK 1  // 1: row-mask formulation of pass 1's S1 (edge_rows); 0: marching scan (scan_tile)
 #endif
 
+#ifndef ZM_S2_TWOWARPS
+#define ZM_S2_TWOWARPS 1  // 1 (needs ZM_S1_ROWMASK): phase B + the row prefixes run in warps 0-1 only, one thread per row
+#endif
+
+#ifndef ZM_S3_REDRAW
+#define ZM_S3_REDRAW 0  // 1: S3 lanes that draw label 0 draw their next label in the same iteration
+#endif
+
 constexpr int TF = 32;  // tile extent along the memory-fastest axis (= one warp per row)
 constexpr int TM = 8;
 constexpr int TS = 8;
@@ -77,8 +85,25 @@ enum : uint32_t {
 // tiles that overflow it are queued and redone by the MODE 1 launch, which processes a tile as two
 // half tiles (4 s-planes each) whose capacities are the hard maxima (so it cannot overflow).
 template <int MODE> struct Caps;
-template <> struct Caps<0> { static constexpr int LT = 128, VCAP = 2048, RCAP = 2048, PROBES = 16, HALVES = 1; };
+#ifndef ZM_CAP0
+#define ZM_CAP0 2048     // MODE 0 capacity (vertex slots / records per tile) of the shared staging arrays
+#endif
+#ifndef ZM_CAP0_U64
+#define ZM_CAP0_U64 1280     // the same for 8-byte labels: 43.3 KB per CTA, which buys the fifth resident CTA (ZM_U64_CTAS)
+#endif
+#ifndef ZM_U64_CTAS
+#define ZM_U64_CTAS 5    // resident CTAs per SM k_classify<8-byte labels, MODE 0> is register-bounded for
+#endif
+#ifndef ZM_U32_CTAS
+#define ZM_U32_CTAS 5    // the same for 1/2/4-byte labels
+#endif
+template <> struct Caps<0> { static constexpr int LT = 128, VCAP = ZM_CAP0, RCAP = ZM_CAP0, PROBES = 16, HALVES = 1; };
 template <> struct Caps<1> { static constexpr int LT = 2048, VCAP = 6 * TILE_VOX / 2, RCAP = 8 * TILE_VOX / 2, PROBES = 2048, HALVES = 2; };
+// staging capacities by label width as well
+template <typename L, int MODE> struct TileCap {
+  static constexpr int V = (MODE == 0 && sizeof(L) == 8) ? ZM_CAP0_U64 : Caps<MODE>::VCAP;
+  static constexpr int R = (MODE == 0 && sizeof(L) == 8) ? ZM_CAP0_U64 : Caps<MODE>::RCAP;
+};
 
 struct VolParams {
   const void* data;        // device pointer, memory order (f fastest, m, s slowest)
@@ -295,21 +320,21 @@ struct __align__(128) P1Smem {
   uint32_t lcnt[Caps<MODE>::LT];   // low 16: vertices of the label in this tile, high 16: triangles
   // per tile-local slot.  MODE 0: local rank (11 bits) | table slot << 11 (7 bits) | voxel-in-tile << 18 | slot << 29;
   // MODE 1: local rank << 12 | table slot, voxel-in-tile | slot << 11 in pstage
-  alignas(16) uint32_t vstage[Caps<MODE>::VCAP];  // (ZM_S1_ROWMASK: holds the row masks of edge_rows until S3)
-  uint32_t rstage[Caps<MODE>::RCAP];  // voxel-in-tile | case << 11 | table slot << 19
+  alignas(16) uint32_t vstage[TileCap<L, MODE>::V];  // (ZM_S1_ROWMASK: holds the row masks of edge_rows until S3)
+  uint32_t rstage[TileCap<L, MODE>::R];  // voxel-in-tile | case << 11 | table slot << 19
   uint32_t tc[4];                  // tile coordinates (tf, tm, ts)
   uint32_t wtot[NW];               // per s-plane: slots | active voxels << 16
   uint32_t nrec, overflow, ok1, ok2, gbase, tlbase, ci, ttot;
   uint16_t alist[TILE_VOX];        // active voxels (voxel-in-tile), compacted
   uint16_t actpre[NROWS];          // active voxels in earlier rows
-  uint16_t pstage[MODE == 0 ? 2 : Caps<MODE>::VCAP];
-  uint16_t rtoff[Caps<MODE>::RCAP];   // per record: first face row inside the (tile,label) block
+  uint16_t pstage[MODE == 0 ? 2 : TileCap<L, MODE>::V];
+  uint16_t rtoff[TileCap<L, MODE>::R];   // per record: first face row inside the (tile,label) block
   alignas(8) uint8_t pp8[NROWS][8];  // slots of the row in lower planes
 };
 static_assert(sizeof(P1Smem<u64, 1>) <= 227 * 1024 && sizeof(P1Smem<uint8_t, 1>) <= 227 * 1024, "dense mode must fit one SM");
-static_assert(sizeof(P1Smem<uint32_t, 0>) <= 44 * 1024 + 400, "MODE 0 / 4-byte labels: five CTAs per SM");
-static_assert(Caps<0>::VCAP <= 2048 && Caps<0>::LT <= 128, "MODE 0 vstage packing");
-static_assert(sizeof(P1Smem<u64, 0>) <= 55 * 1024, "MODE 0 / 8-byte labels: four CTAs per SM");
+static_assert((sizeof(P1Smem<uint32_t, 0>) + 1024) * ZM_U32_CTAS <= 228 * 1024, "MODE 0 / 4-byte labels: ZM_U32_CTAS CTAs per SM (1 KB reserved each)");
+static_assert(Caps<0>::VCAP <= 2048 && ZM_CAP0_U64 <= 2048 && Caps<0>::LT <= 128, "MODE 0 vstage packing");
+static_assert((sizeof(P1Smem<u64, 0>) + 1024) * ZM_U64_CTAS <= 228 * 1024, "MODE 0 / 8-byte labels: ZM_U64_CTAS CTAs per SM (1 KB reserved each)");
 
 extern __shared__ __align__(128) unsigned char zm_dyn_smem[];
 
@@ -479,7 +504,7 @@ template <typename L, int MODE>
 __device__ __forceinline__ void edge_rows(P1Smem<L, MODE>& S, const L* lab) {
   constexpr int RFP = P1Smem<L, MODE>::RFP;
   constexpr uint32_t FULL = 0xffffffffu;
-  static_assert(Caps<MODE>::VCAP >= RS * RM * EM_WORDS, "edge masks overlay vstage");
+  static_assert(TileCap<L, MODE>::V >= RS * RM * EM_WORDS, "edge masks overlay vstage");
   static_assert(NW == TM, "warp w marches over s along the rows m = w");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* const em = S.vstage;
@@ -519,7 +544,7 @@ template <typename L, bool CO, int MODE>
 __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const uint32_t tile,
                                          const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh) {
   constexpr int RFP = P1Smem<L, MODE>::RFP;
-  constexpr int LT = Caps<MODE>::LT, VCAP = Caps<MODE>::VCAP, RCAP = Caps<MODE>::RCAP, PROBES = Caps<MODE>::PROBES;
+  constexpr int LT = Caps<MODE>::LT, VCAP = TileCap<L, MODE>::V, RCAP = TileCap<L, MODE>::R, PROBES = Caps<MODE>::PROBES;
   constexpr uint32_t FULL = 0xffffffffu;
   constexpr int ALIGN = 16 / (int)sizeof(L);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -536,12 +561,18 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
   edge_rows<L, MODE>(S, lab);
   __syncthreads();
   bool any = false;
-  uint32_t packed = 0;  // slots of the row | active voxels of the row << 16   (lane j < TM: row j of the plane)
+  uint32_t packed = 0;  // slots of the row | active voxels of the row << 16   (of the thread's row)
+#if ZM_S2_TWOWARPS
+  const int pw = tid >> 3, pj = tid & 7;  // thread t < NROWS owns row t: plane pw, row pj
+  if (warp < NROWS / 32) {
+#else
+  const int pw = warp, pj = lane;         // lane j < TM of warp w owns row j of plane w
   if (lane < TM) {
-    const int row = warp * TM + lane;
+#endif
+    const int row = pw * TM + pj;
     uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0, act = 0;
-    if (warp >= h0 && warp < h0 + nh) {
-      const uint32_t* e0 = S.vstage + (warp * RM + lane) * EM_WORDS;
+    if (pw >= h0 && pw < h0 + nh) {
+      const uint32_t* e0 = S.vstage + (pw * RM + pj) * EM_WORDS;
       const uint4 q = *reinterpret_cast<const uint4*>(e0);                     // Ef, Em, Es, Z of (m, s)
       const uint32_t zf = e0[4];
       const uint4 qm = *reinterpret_cast<const uint4*>(e0 + EM_WORDS);         // (m + 1, s)
@@ -555,7 +586,7 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
         const uint32_t nfv = vp.Ef - ef0;  // valid columns from ef0 (>= 1)
         const uint32_t VF = nfv >= 32u ? FULL : (1u << nfv) - 1u;          // ef < Ef
         const uint32_t NF1 = nfv >= 33u ? FULL : (1u << (nfv - 1u)) - 1u;  // ef + 1 < Ef
-        const uint32_t em_ = em0 + (uint32_t)lane, es_ = es0 + (uint32_t)warp;
+        const uint32_t em_ = em0 + (uint32_t)pj, es_ = es0 + (uint32_t)pw;
         const bool rowok = em_ < vp.Em && es_ < vp.Es_own;
         const bool nm1 = em_ + 1 < vp.Em, ns1 = es_ + 1 < vp.Es;
         pf = rowok ? pf & NF1 : 0u;
@@ -600,6 +631,27 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     packed = (c4 + __popc(q1.y)) | ((uint32_t)__popc(q1.w) << 16);
   }
 #endif
+#if ZM_S1_ROWMASK && ZM_S2_TWOWARPS
+  // rows 0..31 / 32..63 are scanned by warp 0 / 1; the bases stored before the barrier are relative to the 32-row
+  // group, the readers add the first group's total (wtot[0]) for the rows of the second
+  if (warp < NROWS / 32) {
+    uint32_t rinc = packed;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, rinc, d);
+      if (lane >= d) rinc += t;
+    }
+    const uint32_t ex = rinc - packed;
+    S.pl[tid][6] = ex & 0xFFFFu;
+    S.actpre[tid] = (uint16_t)(ex >> 16);
+    if (lane == 31) S.wtot[warp] = rinc;
+  }
+  if (!__syncthreads_or(any ? 1 : 0)) return TILE_EMPTY;
+  const uint32_t g0 = S.wtot[0];
+  const uint32_t nslots = (g0 + S.wtot[1]) & 0xFFFFu, nact = (g0 + S.wtot[1]) >> 16;
+  if (warp == 1) S.pl[tid][6] += g0 & 0xFFFFu;            // (read by S3 / the flush, after the next barrier)
+  const uint32_t actbase = warp >= NW / 2 ? g0 >> 16 : 0u;  // rows of warps 4..7 = rows 32..63
+#else
   uint32_t rinc = packed;
 #pragma unroll
   for (int d = 1; d < TM; d <<= 1) {
@@ -627,6 +679,8 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
       S.actpre[warp * TM + lane] = (uint16_t)(ex >> 16);
     }
   }
+  const uint32_t actbase = 0u;
+#endif
   if (MODE == 0 && nslots > (uint32_t)VCAP) {
     if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
     return TILE_DEFERRED;
@@ -637,7 +691,7 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
   for (int j = 0; j < TM; ++j) {
     const int row = warp * TM + j;
     const uint32_t mask = S.pl[row][7];
-    if ((mask >> lane) & 1u) S.alist[S.actpre[row] + __popc(mask & ltm)] = (uint16_t)(row * TF + lane);
+    if ((mask >> lane) & 1u) S.alist[actbase + S.actpre[row] + __popc(mask & ltm)] = (uint16_t)(row * TF + lane);
   }
   __syncthreads();
 
@@ -669,6 +723,23 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
 #pragma unroll
       for (int n = 0; n < 8; ++n) msk |= (c[n] == label ? 1u : 0u) << n;
       if (have) acc |= msk;
+#if ZM_S3_REDRAW
+      // lanes that drew the background label (never meshed) draw again right away: one more select + compare
+      // instead of a whole iteration of bookkeeping for nothing.  Volumes without background never take the branch.
+      {
+        const bool redraw = have && label == 0 && acc != 0xFFu;
+        if (__any_sync(FULL, redraw)) {
+          const int start2 = __ffs(~acc & 0xFFu) - 1;
+          L label2 = c[0];
+#pragma unroll
+          for (int n = 1; n < 8; ++n) label2 = (n == start2) ? c[n] : label2;
+          uint32_t msk2 = 0;
+#pragma unroll
+          for (int n = 0; n < 8; ++n) msk2 |= (c[n] == label2 ? 1u : 0u) << n;
+          if (redraw) { label = label2; msk = msk2; acc |= msk2; }
+        }
+      }
+#endif
       const uint32_t cs = ~msk & 0xFFu;
       uint32_t nt = 0, mine = 0;
       if (have && label != 0) {
@@ -845,7 +916,7 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
 #endif
 constexpr uint32_t PREFETCH_DISTANCE = ZM_PREFETCH_TILES;  // tiles ahead (in launch order) whose region is pulled into L2 (0: off)
 template <typename L, bool CO, int MODE>
-__global__ void __launch_bounds__(NT, MODE == 0 ? (sizeof(L) == 8 ? 4 : 5) : 1)
+__global__ void __launch_bounds__(NT, MODE == 0 ? (sizeof(L) == 8 ? ZM_U64_CTAS : ZM_U32_CTAS) : 1)
 k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const Pass1Args o) {
   P1Smem<L, MODE>& S = *reinterpret_cast<P1Smem<L, MODE>*>(zm_dyn_smem);
   const int tid = threadIdx.x;
