@@ -60,6 +60,10 @@ __device__ u64 TRI_NIBBLES_D[256];
 #define ZM_S3_REDRAW 0  // 1: S3 lanes that draw label 0 draw their next label in the same iteration
 #endif
 
+#ifndef ZM_S3_ATOMIC_RANK
+#define ZM_S3_ATOMIC_RANK 0  // 1: S3 ranks vertices / face rows with one shared atomic per lane (prepared for an A/B run)
+#endif
+
 constexpr int TF = 32;  // tile extent along the memory-fastest axis (= one warp per row)
 constexpr int TM = 8;
 constexpr int TS = 8;
@@ -759,6 +763,13 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
       }
       // warp-aggregated add of (nv | nt << 16) to lcnt[hs]; the return value ranks the vertices
       // and gives the record its first face row inside the (tile,label) block
+#if ZM_S3_ATOMIC_RANK
+      // (experiment, not measured yet) let the shared-memory atomic unit serialise the lanes of a label: every
+      // working lane adds its own counts and gets its own rank back -- no match_any / ballots / popcounts
+      uint32_t old = 0;
+      if (work) old = atomicAdd(&S.lcnt[hs], nv | (nt << 16));
+      const uint32_t prev = 0u, pret = 0u;
+#else
       const uint32_t grp = __match_any_sync(FULL, work ? (uint32_t)hs : 0xFFFFFFFFu);
       const uint32_t glt = grp & ltm;
       const uint32_t wv = work ? nv : 0u, wt = work ? nt : 0u;  // nv <= 3, nt <= 5
@@ -771,6 +782,7 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
       uint32_t old = 0;
       if (work && lane == leader) old = atomicAdd(&S.lcnt[hs], tot);
       old = __shfl_sync(FULL, old, leader);
+#endif
       if (work && nv) {
         uint32_t r = (old & 0xFFFFu) + prev;
         uint32_t mm = mine;
