@@ -133,3 +133,35 @@ def test_fanc_fixture_shape():
   assert v.shape == (512, 512, 128, 1) and v.dtype == np.bool_
   assert as_volume3d(v).shape == (512, 512, 128)
   assert as_volume3d(v.T).shape == (1, 128, 512)  # no cube along x: the reference finds no ids
+
+
+def test_get_slices_the_staged_block():
+  """Host logic of Mesher.get (no GPU, no library): per-label views of the one bulk transfer, a private copy
+  when a label is asked for twice, float64 normals, empty meshes for missing / erased / face-less labels."""
+  from zmesh_b200 import mesher as M
+  m = M.Mesher.__new__(M.Mesher)
+  m._voxel_res = np.array((4, 4, 40), dtype=np.float32)
+  m._max_label, m._erased = 2 ** 32 - 1, set()
+  st = M._Stage()
+  st.key = (False, None)
+  st.v = np.arange(30, dtype=np.float32).reshape(10, 3)
+  st.f = np.arange(12, dtype=np.uint32).reshape(4, 3)
+  st.n = np.ones((10, 3), dtype=np.float32)
+  st.index, st.given = {5: (0, 6, 0, 3), 9: (6, 10, 3, 4), 11: (10, 10, 4, 4)}, set()
+  m._stage = st
+  a, b = m.get(5, normals=True), m.get(5, normals=True)
+  assert isinstance(a, Mesh) and a.id == 5 and len(a) == 6 and a.faces.shape == (3, 3)
+  assert a.vertices.dtype == np.float32 and a.faces.dtype == np.uint32
+  assert a.normals.dtype == np.float64 and a.normals.shape == (6, 3)
+  assert a == b and np.shares_memory(a.vertices, st.v) and not np.shares_memory(a.vertices, b.vertices)
+  c = m.get(9)
+  assert c.normals is None and c.id == 9 and np.array_equal(c.vertices, st.v[6:10]) and np.array_equal(c.faces, st.f[3:4])
+  for missing in (11, 12345):
+    e = m.get(missing)
+    assert e.empty() and e.id == missing and e.vertices.shape == (0, 3) and e.faces.shape == (0, 3)
+  m._erased.add(9)
+  assert m.get(9).empty()
+  with pytest.raises(NotImplementedError):
+    m.get(5, reduction_factor=2)
+  with pytest.raises(OverflowError):
+    m.get(2 ** 32)

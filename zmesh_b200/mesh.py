@@ -14,6 +14,9 @@ _PLY_HEADER = (
 )
 
 
+_U32_MAX = int(np.iinfo(np.uint32).max)
+
+
 class Mesh:
   """vertices float32 (Nv,3); faces uint32 (Nf,3) (uint64 only beyond 2^32 vertices);
   normals None or (Nv,3); id = label."""
@@ -21,10 +24,18 @@ class Mesh:
   def __init__(self, vertices=None, faces=None, normals=None, id: Optional[int] = None):
     self.vertices = (np.zeros((0, 3), dtype=np.float32) if vertices is None
                      else np.asarray(vertices, dtype=np.float32))
-    index_t = np.uint64 if self.vertices.shape[0] > np.iinfo(np.uint32).max else np.uint32
+    index_t = np.uint64 if self.vertices.shape[0] > _U32_MAX else np.uint32
     self.faces = np.zeros((0, 3), dtype=index_t) if faces is None else np.asarray(faces, dtype=index_t)
     self.normals = None if normals is None else np.asarray(normals, dtype=np.float32)
     self.id = id
+
+  @classmethod
+  def _wrap(cls, vertices: np.ndarray, faces: np.ndarray, normals, id) -> "Mesh":
+    """Mesh around arrays that already have the final dtypes and shapes (Mesher.get's per-label views): skips
+    the conversions of __init__, which dominate a get() loop over thousands of small labels."""
+    m = cls.__new__(cls)
+    m.vertices, m.faces, m.normals, m.id = vertices, faces, normals, id
+    return m
 
   # -- container protocol ---------------------------------------------------------------------
   @property

@@ -352,11 +352,8 @@ class Mesher:
     if label in st.given:
       v, f = v.copy(), f.copy()
     st.given.add(label)
-    mesh = Mesh(v, f, None)
-    if normals:
-      mesh.normals = st.n[rng[0]:rng[1]].astype(np.float64)  # the reference hands back float64 (zmesh/_zmesh.pyx:151)
-    mesh.id = label
-    return mesh
+    # the reference hands normals back as float64 (zmesh/_zmesh.pyx:151)
+    return Mesh._wrap(v, f, st.n[rng[0]:rng[1]].astype(np.float64) if normals else None, label)
 
   def get_mesh(self, mesh_id, normals=False, simplification_factor=0, max_simplification_error=40,
                voxel_centered=False) -> Mesh:
