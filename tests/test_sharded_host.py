@@ -73,3 +73,15 @@ def test_directory_exchange_gloo_world2():
   assert res[0][1] == [[3, 2 ** 63 + 5, 8], [8, 3]] and res[1][1] == res[0][1]
   assert res[0][2] == [0, 0, 0]
   assert res[1][2] == [2, 7]
+
+
+def test_s1_row_mask_formulation_equals_marching_scan():
+  """Pure-Python restatement of k_classify's two S1 formulations (tools/emulate_s1_rowmask.py): identical bit
+  planes and active-cube masks on random tiles, volume-boundary, zero-fill and slab-shard cases included."""
+  import importlib.util
+  import os
+  from tests.conftest import ROOT
+  spec = importlib.util.spec_from_file_location("emulate_s1_rowmask", os.path.join(ROOT, "tools", "emulate_s1_rowmask.py"))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  assert mod.check(trials=24, seed=7) == 24
