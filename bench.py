@@ -50,13 +50,22 @@ WORKLOADS = {
 }
 
 
-def describe(name, wl, extra=None):
-  d = {"workload": f"{name}: {wl['kind']} {'x'.join(map(str, wl['shape']))} {wl['dtype']} {wl['order']}-order"
-                   + (f" pitch {wl['pitch']}" if 'pitch' in wl else ""),
-       "resolution": list(wl["res"]), "close": wl["close"], "normals": wl["normals"],
-       "voxel_centered": wl["vc"], "reduction_factor": 0}
-  d.update(extra or {})
-  return d
+def describe(name, wl, n_gpus=1):
+  """`config` of the JSON line: names the workload and nothing run-specific, so the product arm and the
+  reference arm print the same object (run-specific facts go to `details` / `cpu_baseline`)."""
+  nb = np.dtype(wl["dtype"]).itemsize
+  per_rank = int(np.prod(wl["shape"])) * nb / max(n_gpus, 1) / 1e9
+  return {"workload": f"{name}: {wl['kind']} {'x'.join(map(str, wl['shape']))} {wl['dtype']} {wl['order']}-order"
+                      + (f" pitch {wl['pitch']}" if 'pitch' in wl else ""),
+          "resolution": list(wl["res"]), "close": wl["close"], "normals": wl["normals"],
+          "voxel_centered": wl["vc"], "reduction_factor": 0,
+          "l2": ("inputs larger than L2 (GPU arm: %.2f GB of labels per rank per step vs 126 MB of L2)" % per_rank
+                 if per_rank > 0.3 else
+                 "GPU arm: L2 flushed between timed steps (a 256 MB buffer is overwritten on the timing stream)"),
+          "sharding": ("single GPU" if n_gpus <= 1 else
+                       f"GPU arm: z-slabs with a 1-plane halo over {n_gpus} ranks, vertices owned by voxel (exactly once "
+                       "across ranks), NCCL all-gather of per-label counts + neighbour send/recv of the boundary plane; "
+                       "results stay distributed")}
 
 
 def load_peaks():
@@ -153,20 +162,59 @@ def device_volume(name, wl, device, zrange=None):
 
 _REF = {}  # inherited by the forked reference workers
 
+# planes of the workload (along its slowest memory axis) the CPU arms time: SURVEY.md 8(d) prescribes the
+# 2048x2048x128 slab for C5; the others are sized for ~5-10 s of single-core reference work per pass.
+CPU_SAMPLE_PLANES = {"c5": 128, "c4": 96, "c5s": 128, "c3": 24}
+# rough single-core rates of the reference (MVx/s) used only to shrink the sample when many passes are asked for
+CPU_RATE = {"c5": 90.0, "c4": 45.0, "c5s": 90.0, "c3": 0.9, "c1": 4.6, "c2a": 300.0, "c2b": 150.0, "c5z": 300.0}
+
+
+def _ref_mesh_all(sample, wl, kind, digest=False):
+  """The reference's own path on `sample`: Mesher.mesh + get for every id.  Returns (faces, {id: digest})."""
+  from oracle import oracle as O
+  m = O.OracleMesher(wl["res"], kind)
+  m.mesh(sample, close=wl["close"])
+  n, dig = 0, {}
+  for i in m.ids():
+    g = m.get(i, normals=wl["normals"], voxel_centered=wl["vc"])
+    n += len(g.faces)
+    if digest:
+      dig[int(i)] = O.multiset_digest(g.vertices, g.faces)
+  return n, dig
+
 
 def _ref_worker(task):
-  """One worker of the reference arm: the unmodified reference (its own Mesher.mesh + get for every id)
-  on planes [lo, hi) of the sample along its slowest memory axis."""
+  """One worker of the reference arm: the unmodified reference on planes [lo, hi) of the sample along its
+  slowest memory axis."""
   lo, hi = task
-  from oracle import oracle as O
   v, wl, kind = _REF["sample"], _REF["wl"], _REF["kind"]
   part = v[:, :, lo:hi] if v.flags.f_contiguous else v[lo:hi]
-  m = O.OracleMesher(wl["res"], kind)
-  m.mesh(part, close=wl["close"])
-  n = 0
-  for i in m.ids():
-    n += len(m.get(i, normals=wl["normals"], voxel_centered=wl["vc"]).faces)
-  return n
+  return _ref_mesh_all(part, wl, kind)[0]
+
+
+def cpu_sample(name, wl, seconds=8.0):
+  """Bounded sample of the workload for the CPU arms (about `seconds` of single-core reference work per pass):
+  the first planes of the volume along its slowest memory axis, as a standalone volume.  Built on the host
+  (numpy / the oracle's C generator) -- never with the product library."""
+  shape = wl["shape"]
+  c_order = wl["order"] == "C"
+  ns = shape[0] if c_order else shape[2]
+  plane = int(np.prod(shape)) // ns
+  want = int(CPU_RATE.get(name, 50.0) * 1e6 * seconds // plane) + 1
+  nz = max(8, min(ns, CPU_SAMPLE_PLANES.get(name, ns), want))
+  sub = (nz, shape[1], shape[2]) if c_order else (shape[0], shape[1], nz)
+  what = f"planes [0,{nz}) of the slowest axis of the workload volume ({'x'.join(map(str, sub))}), meshed as a standalone volume"
+  if wl["kind"] == "voronoi":
+    from oracle.oracle import voronoi_volume_c
+    v = voronoi_volume_c(sub, wl["pitch"], np.dtype(wl["dtype"]), 0, wl["order"], full_shape=shape)
+  elif wl["kind"] == "zeros_device":
+    v = np.zeros(sub, dtype=np.dtype(wl["dtype"]), order=wl["order"])
+  else:
+    full = host_volume(name, wl)
+    v = np.asarray(full[:nz] if c_order else full[:, :, :nz], order=wl["order"])
+  if nz == ns:
+    what = "the full volume"
+  return v, what
 
 
 def run_reference(args, name, wl):
@@ -176,13 +224,14 @@ def run_reference(args, name, wl):
   and never releases the GIL, so one is all the threads it can use).  Beside it,
   `cpu_baseline.all_cores_value` gives what a production harness gets out of the box's cores by running
   one unmodified reference process per core on its own slab of the sample (one halo plane each, partial
-  meshes NOT merged -- the reference has no such step); it is labelled as not a reference feature."""
+  meshes NOT merged -- the reference has no such step); it is labelled as not a reference feature.
+  Nothing of the product (zmesh_b200, its .so, torch) is imported on this arm."""
   import multiprocessing as mp
   from oracle import oracle as O
   O.build()
   kind = "reference" if O.have_reference() else "port"
   nsteps = args.steps + args.warmup
-  sample, sample_desc = cpu_sample(name, wl, seconds=max(2.0, 150.0 / max(nsteps, 1)))
+  sample, sample_desc = cpu_sample(name, wl, seconds=max(1.0, 170.0 / max(nsteps, 1)))
   axis_len = sample.shape[2] if sample.flags.f_contiguous else sample.shape[0]
   _REF.update(sample=sample, wl=wl, kind=kind)
 
@@ -214,45 +263,80 @@ def run_reference(args, name, wl):
     "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
     "scaling": "strong", "vs_baseline": None, "dtype": "u" + str(8 * np.dtype(wl["dtype"]).itemsize),
     "data": "synthetic" if wl["kind"] != "connectomics" else "connectomics.npy (reference sample volume)",
-    "config": describe(name, wl, {"sample": sample_desc}),
+    "config": describe(name, wl, args.gpus),
     "cpu_baseline": {"value": mvx, "unit": "MVx/s", "cores": 1, "kind": kind, "sample": sample_desc, "faces": int(nfaces),
                      "host_cpus": os.cpu_count(), "all_cores_value": all_cores, "all_cores_processes": nproc,
                      "note": "value: the reference as it ships (single-threaded: no threads/SIMD/GIL release; 1 core is all it "
-                             "can use).  all_cores_value: NOT a reference feature -- one unmodified reference process per host "
+                             "can use), each step one pass over the sample, MVx/s = sample voxels / pass time.  "
+                             "all_cores_value: NOT a reference feature -- one unmodified reference process per host "
                              "core, each meshing its own slab of the sample, partial meshes not merged"},
     "e2e": {"value": mvx, "unit": "MVx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
   print(json.dumps(line), flush=True)
 
 
-def cpu_sample(name, wl, seconds=20.0):
-  """Bounded sample of the workload for the CPU arm (about `seconds` of single-core work per pass)."""
-  shape = wl["shape"]
-  if wl["kind"] == "voronoi":
-    # the reference does ~50 MVx/s on one core on the Voronoi workloads
-    nz = max(16, min(shape[2], int(50e6 * seconds // (shape[0] * shape[1])) + 1))
-    try:
-      import torch
-      if torch.cuda.is_available():
-        t = device_volume(name, wl, 0, (0, nz))
-        torch.cuda.synchronize()
-        v = t.cpu().numpy().view(np.dtype(wl["dtype"]))
-        del t
-        return v, f"z-planes [0,{nz}) of the workload volume ({shape[0]}x{shape[1]}x{nz})"
-    except Exception:
-      pass
-    from oracle.oracle import voronoi_volume
-    side = 256
-    v = voronoi_volume((side, side, 64), wl["pitch"], np.dtype(wl["dtype"]), 0, wl["order"], full_shape=shape)
-    return v, f"corner block {side}x{side}x64 of the workload volume (numpy generator, no GPU)"
-  if wl["kind"] == "random":
-    v = host_volume(name, wl, (0, 24))
-    return v, f"z-planes [0,24) of the workload volume ({shape[0]}x{shape[1]}x24)"
-  if wl["kind"] == "connectomics":
-    v = host_volume(name, wl)
-    return v, "the full volume (connectomics.npy 512x512x512)"
-  v = host_volume(name, wl)
-  return v, "full volume"
+def _canon(vertices, faces):
+  """Canonical form of a mesh for the sharded-vs-single-GPU check (vertex rows sorted; faces as vertex rows,
+  rotated to start at their smallest corner, sorted).  A product-vs-product comparison: no oracle involved."""
+  b = np.ascontiguousarray(vertices, dtype=np.float32).view(np.uint32).reshape(-1, 3)
+  cv = b[np.lexsort((b[:, 2], b[:, 1], b[:, 0]))]
+  if len(faces) == 0:
+    return cv.tobytes(), b""
+  order = np.argsort(np.lexsort((b[:, 2], b[:, 1], b[:, 0])))  # rank of every vertex in the sorted list
+  t = order[np.asarray(faces, dtype=np.int64)]
+  k = np.argmin(t, axis=1)
+  idx = (k[:, None] + np.arange(3)[None, :]) % 3
+  r = t[np.arange(len(t))[:, None], idx]
+  r = r[np.lexsort((r[:, 2], r[:, 1], r[:, 0]))]
+  return cv.tobytes(), r.tobytes()
+
+
+def nccl_parity_check(rank, world, local):
+  """N-GPU exactness, run by every rank after the timed region: a 256x256x320 Voronoi volume meshed
+  by the sharded path over NCCL must assemble, label by label, to exactly what ONE GPU produces for the whole
+  volume (close=False, then close=True with normals).  Returns "ok" / "failed: ..." on rank 0."""
+  import torch
+  import torch.distributed as dist
+  from zmesh_b200 import Mesher
+  from zmesh_b200.sharded import ShardedMesher
+  from zmesh_b200.synth import voronoi_device
+  shape, pitch = (256, 256, 320), 40
+  bad, nlab = 0, 0
+  for close in (False, True):
+    sm = ShardedMesher((4, 4, 40), device=local)
+    cube_lo, cube_hi, in_lo, in_hi, last = sm.planes(shape[2], close)
+    slab = voronoi_device((shape[0], shape[1], in_hi - in_lo), pitch, np.uint64, seed=5, order="F",
+                          origin=(0, 0, in_lo), full_shape=shape, device=local)
+    torch.cuda.synchronize()
+    sm.mesh_slab(slab, shape[2], in_lo, close=close, normals=close)
+    ids = sm.all_ids()
+    ref = None
+    if rank == 0:
+      full = voronoi_device(shape, pitch, np.uint64, seed=5, order="F", device=local)
+      torch.cuda.synchronize()
+      ref = Mesher((4, 4, 40), device=local)
+      ref.mesh(full, close=close)
+      if ref.ids() != ids:
+        bad += 1
+    for lbl in ids:
+      got = sm.gather_mesh(lbl, dst=0, normals=close)
+      if rank == 0:
+        want = ref.get(lbl, normals=close)
+        nlab += 1
+        if _canon(got.vertices, got.faces) != _canon(want.vertices, want.faces):
+          bad += 1
+        elif close:  # normals joined on the vertex rows: 1e-5 absolute, equal NaN masks
+          gb = np.ascontiguousarray(got.vertices).view(np.uint32).reshape(-1, 3)
+          wb = np.ascontiguousarray(want.vertices).view(np.uint32).reshape(-1, 3)
+          gn = np.asarray(got.normals)[np.lexsort((gb[:, 2], gb[:, 1], gb[:, 0]))]
+          wn = np.asarray(want.normals)[np.lexsort((wb[:, 2], wb[:, 1], wb[:, 0]))]
+          if not (np.array_equal(np.isnan(gn), np.isnan(wn)) and bool((np.isnan(wn) | (np.abs(gn - wn) <= 1e-5)).all())):
+            bad += 1
+    del sm, slab
+  flag = torch.tensor([bad, nlab], device=f"cuda:{local}")
+  dist.broadcast(flag, 0)
+  bad, nlab = int(flag[0]), int(flag[1])
+  return "ok" if bad == 0 and nlab > 0 else f"failed: {bad} of {nlab} label checks differ"
 
 
 def main():
@@ -265,6 +349,7 @@ def main():
   ap.add_argument("--e2e-steps", type=int, default=2)
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-cpu", action="store_true")
+  ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-single-GPU exactness check after the timed region")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
   name, wl = args.workload, WORKLOADS[args.workload]
@@ -365,9 +450,9 @@ def main():
     ms = float(t.item())
     cnt = torch.tensor([st["n_vertices"], st["n_faces"], st["n_labels"]], device=f"cuda:{dev}", dtype=torch.int64)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    totV, totT = int(cnt[0]), int(cnt[1])
+    totV, totT, nlabels_total = int(cnt[0]), int(cnt[1]), int(cnt[2])  # (labels: summed over ranks, a label spanning k slabs counts k times)
   else:
-    totV, totT = st["n_vertices"], st["n_faces"]
+    totV, totT, nlabels_total = st["n_vertices"], st["n_faces"], st["n_labels"]
   value = nvox_total / 1e6 / (ms / 1e3)
 
   # ---- roofline of the dominant kernel (rank-local averages) -----------------------------------
@@ -385,9 +470,11 @@ def main():
   dom = max(kern, key=lambda k: kern[k][0])
   dom_ms, dom_bytes = kern[dom]
   achieved = dom_bytes / 1e9 / (dom_ms / 1e3) if dom_ms > 0 else 0.0
+  # DRAM bytes per launch of the dominant kernel from the ncu capture of the CURRENT kernels kept in
+  # profiles/traffic.json (keyed by workload; single-GPU launches only -- a rank-local slab moves 1/N of it)
   traffic = None
   tp = os.path.join(ROOT, "profiles", "traffic.json")
-  if os.path.exists(tp):
+  if world == 1 and os.path.exists(tp):
     try:
       traffic = json.load(open(tp)).get(name, {}).get(dom)
     except Exception:
@@ -418,20 +505,33 @@ def main():
       pinned = None
     d2h = 0
 
+    phase = {"mesh_call_ms": 0.0, "get_loop_ms": 0.0, "h2d_ms": 0.0, "classify_ms": 0.0, "emit_ms": 0.0}
+
     def e2e_step():
       nonlocal d2h
+      t_a = time.perf_counter()
       if world > 1:
         sm.mesh_slab(hnp, shape[2], zr[0], close=wl["close"], finalize=wl["normals"], voxel_centered=wl["vc"],
                      normals=wl["normals"])
       else:
         mesher.mesh(hnp, close=wl["close"])
+      t_b = time.perf_counter()
       d2h = 0
       for i in mesher.ids():
         m = mesher.get(i, normals=wl["normals"], reduction_factor=0, voxel_centered=wl["vc"])
         d2h += m.vertices.nbytes + m.faces.nbytes + (m.vertices.nbytes if wl["normals"] else 0)
+      t_c = time.perf_counter()
+      s2 = mesher.stats()
+      phase["mesh_call_ms"] += (t_b - t_a) * 1e3
+      phase["get_loop_ms"] += (t_c - t_b) * 1e3  # first get(): pass 2 on the device + ONE bulk D2H; the rest are host slices
+      phase["h2d_ms"] += s2["ms_h2d"]
+      phase["classify_ms"] += s2["ms_classify"] + s2["ms_scan"]
+      phase["emit_ms"] += s2["ms_finalize"]
 
     e2e_step()  # warm-up (allocations, page faults)
     barrier()
+    for k in phase:
+      phase[k] = 0.0
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
       e2e_step()
@@ -444,22 +544,42 @@ def main():
     e2e = {"value": nvox_total / 1e6 / dt, "unit": "MVx/s", "h2d_bytes_per_step": int(hnp.nbytes),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
            "host_buffer": "cudaHostRegister'ed numpy" if pinned is not None else "pageable numpy",
+           "phases_ms": {k: v / args.e2e_steps for k, v in phase.items()},
+           "pcie_gbs": {"h2d": (hnp.nbytes / 1e9) / (phase["h2d_ms"] / args.e2e_steps / 1e3) if phase["h2d_ms"] > 0 else None},
            "api": "zmesh_b200.Mesher.mesh(ndarray) + get(id) for every id (rank-local slab when sharded)"}
 
-  # ---- CPU baseline beside it (rank 0, N = 1) ---------------------------------------------------
+  # ---- CPU baseline beside it (rank 0, N = 1): the compiled reference on one host core, two passes over a
+  #      bounded sample (the second, warm one is reported), and the SAME sample through the product path with
+  #      per-label fingerprints compared (bit-exact vertex / face sets; oracle.multiset_digest) ---------------
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu:
     from oracle import oracle as O
     kind = "reference" if O.have_reference() else "port"
     sample, sdesc = cpu_sample(name, wl)
-    t0 = time.perf_counter()
-    m = O.OracleMesher(wl["res"], kind)
-    m.mesh(sample, close=wl["close"])
-    for i in m.ids():
-      m.get(i, normals=wl["normals"], voxel_centered=wl["vc"])
-    dt = time.perf_counter() - t0
-    cpu = {"value": sample.size / 1e6 / dt, "unit": "MVx/s", "cores": 1, "kind": kind, "sample": sdesc,
-           "seconds": dt, "host_cpus": os.cpu_count()}
+    secs = []
+    for _ in range(2):
+      t0 = time.perf_counter()
+      nfaces, _ = _ref_mesh_all(sample, wl, kind)
+      secs.append(time.perf_counter() - t0)
+    _, want = _ref_mesh_all(sample, wl, kind, digest=True)
+    mesher.set_stream(None)
+    mesher.mesh(sample, close=wl["close"])
+    got_ids = [int(i) for i in mesher.ids()]
+    mism = 0 if sorted(got_ids) == sorted(want) else 1
+    for i in got_ids:
+      g = mesher.get(i, normals=False, voxel_centered=wl["vc"])
+      if O.multiset_digest(g.vertices, g.faces) != want.get(i):
+        mism += 1
+    cpu = {"value": sample.size / 1e6 / secs[1], "unit": "MVx/s", "cores": 1, "kind": kind, "sample": sdesc,
+           "seconds": secs[1], "seconds_cold_pass": secs[0], "passes": 2, "faces": int(nfaces), "host_cpus": os.cpu_count(),
+           "parity_on_sample": mism == 0, "parity_labels": len(want), "parity_mismatches": mism,
+           "parity_note": "the sample meshed by the GPU path through the drop-in API; per-label fingerprints of the "
+                          "vertex and face sets (rotation-invariant, winding-sensitive) equal to the compiled reference's"}
+
+  nccl_parity = None
+  if world > 1 and not args.no_parity:
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    nccl_parity = nccl_parity_check(rank, world, local_rank)
 
   if rank == 0:
     line = {
@@ -467,13 +587,10 @@ def main():
       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
       "dtype": "u" + str(8 * label_bytes),
       "data": "synthetic" if wl["kind"] != "connectomics" else "connectomics.npy (reference sample volume)",
-      "config": describe(name, wl, {
-        "l2": "inputs larger than L2 (volume %.1f GB per rank >> 126 MB)" % (nvox_local * label_bytes / 1e9),
-        "sharding": (f"z-slabs with 1-plane halo over {world} ranks; vertices owned by voxel (exactly once across "
-                     "ranks), face indices made global by an all-gather of per-label counts + a neighbour "
-                     "send/recv of the boundary plane (NCCL); results stay distributed") if world > 1 else "single GPU",
-        "labels": int(st["n_labels"]), "vertices": int(totV), "faces": int(totT),
-        "tiles": {"all": int(st["n_tiles"]), "non_empty": int(st["n_active_tiles"]), "dense_redo": int(st["n_dense_tiles"])}}),
+      "config": describe(name, wl, world),
+      "details": {"labels": int(nlabels_total), "vertices": int(totV), "faces": int(totT), "volume_gb_per_rank": nvox_local * label_bytes / 1e9,
+                  "tiles": {"all": int(st["n_tiles"]), "non_empty": int(st["n_active_tiles"]), "dense_redo": int(st["n_dense_tiles"])}},
+      "parity_on_sample": (cpu or {}).get("parity_on_sample"), "nccl_parity": nccl_parity,
       "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
       "clocks": clocks.summary(),
     }

@@ -61,6 +61,8 @@ def _port():
     L.zo_erase.argtypes = [C.c_void_p, C.c_uint64]
     L.zo_get.argtypes = [C.c_void_p, C.c_uint64, C.c_int, _u64p, _u64p, _f32p, _u32p]
     L.zo_normals.argtypes = [_f32p, C.c_uint64, _u32p, C.c_uint64, _f32p]
+    L.zo_voronoi.restype = None
+    L.zo_voronoi.argtypes = [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, C.c_uint32, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64]
     _libs["port"] = L
   return _libs["port"]
 
@@ -255,6 +257,30 @@ def canonical_digest(vertices: np.ndarray, faces: np.ndarray) -> str:
   return h.hexdigest()
 
 
+def _mix64(x):
+  x = np.asarray(x, dtype=np.uint64)
+  with np.errstate(over="ignore"):
+    x = (x ^ (x >> np.uint64(33))) * np.uint64(0xFF51AFD7ED558CCD)
+    x = (x ^ (x >> np.uint64(33))) * np.uint64(0xC4CEB9FE1A85EC53)
+    return x ^ (x >> np.uint64(33))
+
+
+def multiset_digest(vertices: np.ndarray, faces: np.ndarray):
+  """O(n) order-independent fingerprint of a mesh, for volumes whose canonical (sorted) form is too slow to build:
+  (V, sum and xor of a 64-bit hash per vertex row, T, sum and xor of a hash per face), where the face hash is
+  invariant under rotation of its three corners and changes under reflection (winding) -- the same equivalence
+  as canonical_faces.  Equal digests of a mesh without duplicate vertices <=> equal canonical sets, up to 2^-64."""
+  b = np.ascontiguousarray(vertices, dtype=np.float32).view(np.uint32).reshape(-1, 3).astype(np.uint64)
+  with np.errstate(over="ignore"):
+    hv = _mix64(b[:, 0] * np.uint64(0x9E3779B97F4A7C15) + _mix64(b[:, 1] * np.uint64(0xC2B2AE3D27D4EB4F) + _mix64(b[:, 2] + np.uint64(0x165667B19E3779F9))))
+    f = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+    ha, hb, hc = hv[f[:, 0]], hv[f[:, 1]], hv[f[:, 2]]
+    pair = lambda x, y: _mix64(x * np.uint64(0x9E3779B97F4A7C15) + (y ^ np.uint64(0xD6E8FEB86659FD93)))
+    hf = _mix64(pair(ha, hb) + pair(hb, hc) + pair(hc, ha))
+    return (int(len(b)), int(hv.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(hv)) if len(hv) else 0,
+            int(len(f)), int(hf.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(hf)) if len(hf) else 0)
+
+
 def assert_same_mesh(got, want, normals_tol: float = 1e-5, what: str = ""):
   """Bit-exact canonical vertex and face sets; normals joined on vertex rows within tolerance."""
   gv, wv = canonical_vertices(got.vertices), canonical_vertices(want.vertices)
@@ -334,6 +360,32 @@ def voronoi_volume(shape, pitch: int, dtype=np.uint64, seed: int = 0, order: str
   else:
     lab = (best_c + 1).astype(dtype)
   return np.asarray(lab, dtype=dtype, order=order)
+
+
+def voronoi_volume_c(shape, pitch: int, dtype=np.uint64, seed: int = 0, order: str = "F",
+                     origin=(0, 0, 0), full_shape=None, threads: int = 0) -> np.ndarray:
+  """voronoi_volume computed by the C restatement (oracle/zmesh_oracle.c:zo_voronoi), split over host
+  threads along the slowest memory axis (ctypes releases the GIL).  Bit-identical to voronoi_volume and to
+  the device generator; exists so that bench.py's CPU arms can build C4/C5-sized samples in seconds
+  without loading the product library."""
+  from concurrent.futures import ThreadPoolExecutor
+  L = _port()
+  shape = tuple(int(s) for s in shape)
+  full_shape = tuple(int(s) for s in (full_shape or shape))
+  out = np.empty(shape, dtype=np.dtype(dtype), order=order)
+  c_order = 1 if order == "C" else 0
+  a3 = lambda t: (C.c_uint64 * 3)(*[int(x) for x in t])
+  sh, og, fs = a3(shape), a3(origin), a3(full_shape)
+  ns = shape[0] if c_order else shape[2]
+  nthreads = max(1, min(threads or (os.cpu_count() or 1), ns))
+  cuts = [ns * k // nthreads for k in range(nthreads + 1)]
+  nb = np.dtype(dtype).itemsize
+
+  def work(k):
+    L.zo_voronoi(C.c_void_p(out.ctypes.data), nb, sh, og, fs, int(pitch), int(seed), c_order, cuts[k], cuts[k + 1])
+  with ThreadPoolExecutor(nthreads) as ex:
+    list(ex.map(work, range(nthreads)))
+  return out
 
 
 def random_volume(shape, nlabels: int = 1000, dtype=np.uint32, seed: int = 0, order: str = "C") -> np.ndarray:

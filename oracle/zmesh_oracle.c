@@ -308,3 +308,76 @@ void zo_normals(const float* vertices, uint64_t nv, const uint32_t* faces, uint6
   }
   for (uint64_t i = 0; i < nv; ++i) v_hat(out + 3 * i); /* (:372-381) */
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic jittered-grid Voronoi volume (the same integer definition as
+ * oracle.py:voronoi_volume and the device generator).  Test / benchmark input only: lets the CPU arm
+ * of bench.py build its sample without touching the product library.  Fills planes [p0, p1) of the
+ * block along its slowest memory axis, so callers can split a block over threads. */
+static uint64_t zo_splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  uint64_t z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+void zo_voronoi(void* dst, int label_bytes, const uint64_t shape[3], const uint64_t origin[3],
+                const uint64_t full_shape[3], uint32_t pitch, uint64_t seed, int c_order, uint64_t p0, uint64_t p1) {
+  const int64_t P = (int64_t)pitch;
+  int64_t G[3];
+  for (int a = 0; a < 3; ++a) {
+    G[a] = (int64_t)((full_shape[a] + pitch - 1) / pitch);
+    if (G[a] < 1) G[a] = 1;
+  }
+  /* memory axes: f fastest, s slowest */
+  const int af = c_order ? 2 : 0, as = c_order ? 0 : 2;
+  const uint64_t nf = shape[af], nm = shape[1];
+  for (uint64_t ps = p0; ps < p1; ++ps)
+    for (uint64_t pm = 0; pm < nm; ++pm) {
+      int64_t q[3];
+      q[as] = (int64_t)(ps + origin[as]);
+      q[1] = (int64_t)(pm + origin[1]);
+      const int64_t bs = q[as] / P, bm = q[1] / P;
+      int64_t last_bf = -1;
+      int64_t sx[27], sy[27], sz[27], sc[27];
+      int ns = 0;
+      for (uint64_t pf = 0; pf < nf; ++pf) {
+        q[af] = (int64_t)(pf + origin[af]);
+        const int64_t bf = q[af] / P;
+        if (bf != last_bf) { /* sites of the 27 neighbouring cells, in the order (dk, dj, di) of the definition */
+          last_bf = bf;
+          int64_t b[3];
+          b[af] = bf; b[1] = bm; b[as] = bs;
+          ns = 0;
+          for (int dk = -1; dk <= 1; ++dk)
+            for (int dj = -1; dj <= 1; ++dj)
+              for (int di = -1; di <= 1; ++di) {
+                const int64_t ni = b[0] + di, nj = b[1] + dj, nk = b[2] + dk;
+                if (ni < 0 || nj < 0 || nk < 0 || ni >= G[0] || nj >= G[1] || nk >= G[2]) continue;
+                const uint64_t c = (uint64_t)ni + (uint64_t)G[0] * ((uint64_t)nj + (uint64_t)G[1] * (uint64_t)nk);
+                const uint64_t h = zo_splitmix64(c ^ seed);
+                sx[ns] = ni * P + (int64_t)(((h & 0xFFFFull) * (uint64_t)P) >> 16);
+                sy[ns] = nj * P + (int64_t)((((h >> 16) & 0xFFFFull) * (uint64_t)P) >> 16);
+                sz[ns] = nk * P + (int64_t)((((h >> 32) & 0xFFFFull) * (uint64_t)P) >> 16);
+                sc[ns] = (int64_t)c;
+                ++ns;
+              }
+        }
+        int64_t best_d = INT64_MAX, best_c = 0;
+        for (int i = 0; i < ns; ++i) {
+          const int64_t dx = q[0] - sx[i], dy = q[1] - sy[i], dz = q[2] - sz[i];
+          const int64_t d = dx * dx + dy * dy + dz * dz;
+          if (d < best_d || (d == best_d && sc[i] < best_c)) { best_d = d; best_c = sc[i]; }
+        }
+        const uint64_t lab = label_bytes == 8 ? (zo_splitmix64((uint64_t)best_c + 1ull) | 1ull) : (uint64_t)best_c + 1ull;
+        const size_t i = ((size_t)ps * nm + pm) * nf + pf;
+        switch (label_bytes) {
+          case 1: ((uint8_t*)dst)[i] = (uint8_t)lab; break;
+          case 2: ((uint16_t*)dst)[i] = (uint16_t)lab; break;
+          case 4: ((uint32_t*)dst)[i] = (uint32_t)lab; break;
+          default: ((uint64_t*)dst)[i] = lab; break;
+        }
+      }
+    }
+}

@@ -23,6 +23,8 @@ NVCC_FLAGS = [
 def build(force: bool = False, verbose: bool = False) -> str:
   """Compile the CUDA library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
   srcs = SOURCES + [HEADER]
+  if os.environ.get("ZMESH_B200_LIB"):  # a development build selected by hand is used as it is, never rebuilt
+    return LIB_PATH
   if not force and os.path.exists(LIB_PATH):
     if all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs if os.path.exists(s)):
       return LIB_PATH

@@ -60,8 +60,12 @@ __device__ u64 TRI_NIBBLES_D[256];
 #define ZM_S3_REDRAW 0  // 1: S3 lanes that draw label 0 draw their next label in the same iteration
 #endif
 
+#ifndef ZM_K2_PATH
+#define ZM_K2_PATH 1  // 1: MODE 0 tiles whose staged region holds exactly two labels take the bit-parallel two-label path (tile_body<.., K2 = true>)
+#endif
+
 #ifndef ZM_S3_ATOMIC_RANK
-#define ZM_S3_ATOMIC_RANK 0  // 1: S3 ranks vertices / face rows with one shared atomic per lane (prepared for an A/B run)
+#define ZM_S3_ATOMIC_RANK 1  // 1: S3 ranks vertices / face rows with one shared atomic per working lane (c1 k_classify 1.24 -> 1.05 ms, c5 31.5 -> 30.2); 0: match_any + REDUX + five ballots
 #endif
 
 constexpr int TF = 32;  // tile extent along the memory-fastest axis (= one warp per row)
@@ -402,28 +406,45 @@ __device__ __forceinline__ void stage_plain(const VolParams& vp, P1Smem<L, MODE>
   }
 }
 
-// true iff every staged element equals the first one (then no cube of the tile is active and no
-// voxel owns a slot); 16-byte compares, one barrier
+// true iff every staged element equals the first element of the region (then no cube of the tile is active and
+// no voxel owns a slot); 16-byte compares, one barrier.  On a non-uniform region every thread that met a different
+// element publishes one such label in S.recbase (any one writer wins): the second label of the two-label path.
 template <typename L, int MODE>
-__device__ __forceinline__ bool region_uniform(const P1Smem<L, MODE>& S) {
+__device__ __forceinline__ bool region_uniform(P1Smem<L, MODE>& S, const L* lab, L& first, L& second) {
   constexpr int NQ = (int)sizeof(L) * RS * RM * P1Smem<L, MODE>::RFP / 16;
+  constexpr int PER = 16 / (int)sizeof(L);
   const uint4* q = reinterpret_cast<const uint4*>(S.lab);
+  first = lab[0];
   uint4 ref;
   if (sizeof(L) == 8) {
-    const uint2 r = *reinterpret_cast<const uint2*>(S.lab);
-    ref = make_uint4(r.x, r.y, r.x, r.y);
+    const u64 r = (u64)first;
+    ref = make_uint4((uint32_t)r, (uint32_t)(r >> 32), (uint32_t)r, (uint32_t)(r >> 32));
   } else {
-    uint32_t r = *reinterpret_cast<const uint32_t*>(S.lab);
+    uint32_t r = (uint32_t)first;
     if (sizeof(L) == 2) r = __byte_perm(r, r, 0x1010);
     if (sizeof(L) == 1) r = __byte_perm(r, r, 0x0000);
     ref = make_uint4(r, r, r, r);
   }
   uint32_t acc = 0;
+  int at = 0;
   for (int i = threadIdx.x; i < NQ; i += NT) {
     const uint4 v = q[i];
-    acc |= (v.x ^ ref.x) | (v.y ^ ref.y) | (v.z ^ ref.z) | (v.w ^ ref.w);
+    const uint32_t d = (v.x ^ ref.x) | (v.y ^ ref.y) | (v.z ^ ref.z) | (v.w ^ ref.w);
+    acc |= d;
+    if (d) at = i;
   }
-  return __syncthreads_and(acc == 0u) != 0;
+#if ZM_K2_PATH
+  if (MODE == 0 && acc) {
+    const L* e = S.lab + at * PER;
+    L other = e[0];
+#pragma unroll
+    for (int j = 1; j < PER; ++j) other = (other == first) ? e[j] : other;
+    S.recbase = (u64)other;
+  }
+#endif
+  const bool uni = __syncthreads_and(acc == 0u) != 0;
+  second = (L)S.recbase;
+  return uni;
 }
 
 // all-zero rowinfo for the row segments of planes [h0, h0 + nh) of a tile without slots
@@ -540,13 +561,47 @@ __device__ __forceinline__ void edge_rows(P1Smem<L, MODE>& S, const L* lab) {
   }
 }
 
-enum : int { TILE_EMPTY = 0, TILE_DEFERRED = 1, TILE_DONE = 2 };
+// Two-label path, S1: the staged region holds (at most) the labels A and B, so ONE 33-bit mask per staged row
+// -- bit f = (voxel f carries A) -- says everything: edges are where the mask changes, the non-zero masks follow
+// from which of A / B is the background.  One compare pair + one ballot per row instead of edge_rows' three label
+// compares + five ballots per voxel.  Returns true when a voxel outside {A, B} was met (the tile then takes the
+// general path).  The masks live in S.lkeys[2 ..] (64-bit, bit 32 = the +f halo column); lkeys[0 / 1] hold A / B.
+constexpr int K2_MASK0 = 2;  // first lkeys entry used for the row masks
+template <typename L, int MODE>
+__device__ __forceinline__ bool k2_rows(P1Smem<L, MODE>& S, const L* lab, const L A, const L B) {
+  constexpr int RFP = P1Smem<L, MODE>::RFP;
+  constexpr uint32_t FULL = 0xffffffffu;
+  static_assert(Caps<MODE>::LT >= K2_MASK0 + RS * RM, "row masks overlay the label keys");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* const mw = reinterpret_cast<uint32_t*>(S.lkeys + K2_MASK0);
+  bool bad = false;
+#pragma unroll 3
+  for (int r = warp; r < RS * RM; r += NW) {
+    const L a = lab[r * RFP + lane];
+    const bool pa = a == A;
+    bad |= !(pa || a == B);
+    const uint32_t m = __ballot_sync(FULL, pa);
+    if (lane == 0) mw[2 * r] = m;
+  }
+  if (threadIdx.x < RS * RM) {  // the +f halo column
+    const L a = lab[threadIdx.x * RFP + TF];
+    const bool pa = a == A;
+    bad |= !(pa || a == B);
+    mw[2 * threadIdx.x + 1] = pa ? 1u : 0u;
+  }
+  return bad;
+}
+
+enum : int { TILE_EMPTY = 0, TILE_DEFERRED = 1, TILE_DONE = 2, TILE_NOT_K2 = 3 };
 
 // Everything after staging for planes [h0, h0 + nh) of a tile (all 8 in MODE 0).  The caller has
 // staged the region and synchronised; the per-tile tables are cleared here.
-template <typename L, bool CO, int MODE>
+template <typename L, bool CO, int MODE, bool K2 = false>
 __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const uint32_t tile,
-                                         const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh) {
+                                         const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh,
+                                         const L keyA = 0, const L keyB = 0) {
+  static_assert(!K2 || (MODE == 0 && ZM_S1_ROWMASK && ZM_S2_TWOWARPS), "the two-label path is a MODE 0 / row-mask variant");
+  constexpr int LTU = K2 ? 2 : Caps<MODE>::LT;  // label-table entries in use
   constexpr int RFP = P1Smem<L, MODE>::RFP;
   constexpr int LT = Caps<MODE>::LT, VCAP = TileCap<L, MODE>::V, RCAP = TileCap<L, MODE>::R, PROBES = Caps<MODE>::PROBES;
   constexpr uint32_t FULL = 0xffffffffu;
@@ -556,14 +611,22 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
   const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
   const L* const lab = S.lab + (vp.pad ? ALIGN - 1 : 0);
 
-  for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
+  if (K2) {
+    if (tid < 2) { S.lkeys[tid] = (u64)(tid == 0 ? keyA : keyB); S.lcnt[tid] = 0u; }
+  } else {
+    for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
+  }
   if (tid == 0) { S.nrec = 0; S.overflow = 0; S.ci = 0; S.ttot = 0; }
 
 #if ZM_S1_ROWMASK
   // ---- S1 (row masks): phase A: edge / non-zero masks of all staged rows; phase B: lane j < TM of warp w turns
   //      them into the bit planes and the active-cube mask of row (w, j), then S2's in-row prefixes ----
-  edge_rows<L, MODE>(S, lab);
-  __syncthreads();
+  if (K2) {
+    if (__syncthreads_or(k2_rows<L, MODE>(S, lab, keyA, keyB) ? 1 : 0)) return TILE_NOT_K2;
+  } else {
+    edge_rows<L, MODE>(S, lab);
+    __syncthreads();
+  }
   bool any = false;
   uint32_t packed = 0;  // slots of the row | active voxels of the row << 16   (of the thread's row)
 #if ZM_S2_TWOWARPS
@@ -576,12 +639,27 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     const int row = pw * TM + pj;
     uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0, act = 0;
     if (pw >= h0 && pw < h0 + nh) {
-      const uint32_t* e0 = S.vstage + (pw * RM + pj) * EM_WORDS;
-      const uint4 q = *reinterpret_cast<const uint4*>(e0);                     // Ef, Em, Es, Z of (m, s)
-      const uint32_t zf = e0[4];
-      const uint4 qm = *reinterpret_cast<const uint4*>(e0 + EM_WORDS);         // (m + 1, s)
-      const uint4 qs = *reinterpret_cast<const uint4*>(e0 + RM * EM_WORDS);    // (m, s + 1)
-      const uint32_t ef3 = e0[(RM + 1) * EM_WORDS];                            // Ef of (m + 1, s + 1)
+      uint4 q, qm, qs;  // Ef, Em, Es, Z of rows (m, s), (m + 1, s), (m, s + 1)
+      uint32_t zf, ef3;  // non-zero mask of the +f neighbours of (m, s); Ef of (m + 1, s + 1)
+      if (K2) {
+        const u64* mk = S.lkeys + K2_MASK0 + (pw * RM + pj);
+        const u64 m00 = mk[0], m10 = mk[1], m01 = mk[RM], m11 = mk[RM + 1];
+        const bool zA = keyA == 0, zB = keyB == 0;  // (at most one of the two is the background)
+        auto nz = [&](uint32_t isA) { return zA ? ~isA : (zB ? isA : 0xffffffffu); };
+        q.x = (uint32_t)(m00 ^ (m00 >> 1)); q.y = (uint32_t)(m00 ^ m10); q.z = (uint32_t)(m00 ^ m01); q.w = nz((uint32_t)m00);
+        zf = nz((uint32_t)(m00 >> 1));
+        qm.x = (uint32_t)(m10 ^ (m10 >> 1)); qm.w = nz((uint32_t)m10);
+        qs.x = (uint32_t)(m01 ^ (m01 >> 1)); qs.y = (uint32_t)(m01 ^ m11); qs.w = nz((uint32_t)m01);
+        qm.y = qm.z = qs.z = 0u;
+        ef3 = (uint32_t)(m11 ^ (m11 >> 1));
+      } else {
+        const uint32_t* e0 = S.vstage + (pw * RM + pj) * EM_WORDS;
+        q = *reinterpret_cast<const uint4*>(e0);
+        zf = e0[4];
+        qm = *reinterpret_cast<const uint4*>(e0 + EM_WORDS);
+        qs = *reinterpret_cast<const uint4*>(e0 + RM * EM_WORDS);
+        ef3 = e0[(RM + 1) * EM_WORDS];
+      }
       const uint32_t nonuni = q.x | qm.x | qs.x | ef3 | q.y | qs.y | q.z;     // cube has two different corners
       uint32_t pf = q.x, pm = q.y, ps = q.z, cube = nonuni;
       if (!(ef0 + TF + 1 <= vp.Ef && em0 + TM + 1 <= vp.Em && es0 + TS + 1 <= vp.Es)) {
@@ -705,10 +783,6 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     const bool valid = i < nact;
     const uint32_t vidx = valid ? S.alist[i] : 0u;
     const int lf = vidx & 31, lm = (vidx >> 5) & 7, ls = vidx >> 8;
-    L c[8];
-#pragma unroll
-    for (int n = 0; n < 8; ++n)
-      c[n] = lab[((ls + corner_ds<CO>(n)) * RM + (lm + corner_dm<CO>(n))) * RFP + (lf + corner_df<CO>(n))];
     // slots exist only on edges whose upper voxel is inside the (extended) volume
     const bool axf = ef0 + lf + 1 < vp.Ef, axm = em0 + lm + 1 < vp.Em, axs = es0 + ls + 1 < vp.Es;
     const uint32_t amask = (axf ? 0x03u : 0u) | (axm ? 0x0Cu : 0u) | (axs ? 0x30u : 0u);
@@ -716,6 +790,65 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     const uint32_t row = vidx >> 5;
     const uint32_t ltf = (1u << lf) - 1u;
     const uint32_t rowpre = S.pl[row][6];
+    if constexpr (K2) {
+      // corner mask of label A straight from the four row masks; B's is the complement.  Every lane of the warp
+      // works on the same label, so its counter is the only address the shared atomic sees.
+      const u64* mk = S.lkeys + K2_MASK0 + (ls * RM + lm);
+      uint32_t b[4];  // index dm + 2 * ds: bits (f, f + 1) of the row
+      b[0] = (uint32_t)(mk[0] >> lf) & 3u; b[1] = (uint32_t)(mk[1] >> lf) & 3u;
+      b[2] = (uint32_t)(mk[RM] >> lf) & 3u; b[3] = (uint32_t)(mk[RM + 1] >> lf) & 3u;
+      uint32_t mskA = 0;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) mskA |= ((b[corner_dm<CO>(n) + 2 * corner_ds<CO>(n)] >> corner_df<CO>(n)) & 1u) << n;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if ((k == 0 ? keyA : keyB) == 0) continue;  // the background is never meshed (uniform branch)
+        const uint32_t msk = k == 0 ? mskA : (~mskA & 0xFFu);
+        const uint32_t cs = ~msk & 0xFFu;
+        uint32_t nt = 0, mine = 0;
+        if (valid) {
+          if (cube) nt = __ldg(&TRI_COUNT_D[cs]);
+          const uint32_t nb = ((msk >> corner_plus_f<CO>()) & 1u) | (((msk >> corner_plus_m<CO>()) & 1u) << 2) |
+                              (((msk >> corner_plus_s<CO>()) & 1u) << 4);
+          mine = ((msk & 1u) ? (0x15u & ~nb) : (nb << 1)) & amask;
+        }
+        const uint32_t nv = __popc(mine);
+        const bool work = (nv | nt) != 0u;
+        uint32_t old = 0;
+        if (work) old = atomicAdd(&S.lcnt[k], nv | (nt << 16));
+        if (nv) {
+          uint32_t r = old & 0xFFFFu;
+          uint32_t mm = mine;
+          while (mm) {
+            const int s6 = __ffs(mm) - 1;
+            mm &= mm - 1u;
+            const uint32_t lg = rowpre + S.pp8[row][s6] + __popc(S.pl[row][s6] & ltf);
+            S.vstage[lg] = r | ((uint32_t)k << 11) | (vidx << 18) | ((uint32_t)s6 << 29);
+            ++r;
+          }
+        }
+        const bool hasrec = nt != 0u;
+        const uint32_t rb = __ballot_sync(FULL, hasrec);
+        if (rb) {
+          uint32_t rbase = 0;
+          if (lane == 0) rbase = atomicAdd(&S.nrec, (uint32_t)__popc(rb));
+          rbase = __shfl_sync(FULL, rbase, 0);
+          if (hasrec) {
+            const uint32_t pos = rbase + __popc(rb & ltm);
+            if (pos < (uint32_t)RCAP) {
+              S.rstage[pos] = vidx | (cs << 11) | ((uint32_t)k << 19);
+              S.rtoff[pos] = (uint16_t)(old >> 16);
+            } else {
+              S.overflow = 1u;
+            }
+          }
+        }
+      }
+    } else {
+    L c[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      c[n] = lab[((ls + corner_ds<CO>(n)) * RM + (lm + corner_dm<CO>(n))) * RFP + (lf + corner_df<CO>(n))];
     uint32_t acc = valid ? 0u : 0xFFu;
     while (__any_sync(FULL, acc != 0xFFu)) {
       const bool have = acc != 0xFFu;
@@ -816,6 +949,7 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
         }
       }
     }
+    }  // (general path)
   }
   __syncthreads();  // the staged labels are dead from here on (lvb / cidx reuse their memory)
   if (S.overflow) {
@@ -838,8 +972,9 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     S.recbase = recbase;
     S.ok1 = ok ? 1u : 0u;
   }
-  for (int i = tid; i < LT; i += NT) {
-    const u64 label = S.lkeys[i];
+  for (int i = tid; i < LTU; i += NT) {
+    u64 label = S.lkeys[i];
+    if (K2 && label != 0ull && S.lcnt[i] == 0u) S.lkeys[i] = label = 0ull;  // (present in the region, nothing to mesh here)
     if (label != 0ull) {
       const uint32_t cnt = S.lcnt[i];
       const uint32_t nv = cnt & 0xFFFFu, nt = cnt >> 16;
@@ -910,7 +1045,7 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
   __syncthreads();
   if (!S.ok2) return TILE_DONE;
   const uint32_t tlbase = S.tlbase;
-  for (int i = tid; i < LT; i += NT) {
+  for (int i = tid; i < LTU; i += NT) {
     if (S.lkeys[i] != 0ull) {
       TLEntry e;
       e.a = S.tla[i];
@@ -936,7 +1071,7 @@ k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const P
     mbar_init(&S.mbar, 1);
     fence_mbar_init();
   }
-  if (MODE == 0) {
+  if constexpr (MODE == 0) {
     if (tid == 0) {
       uint32_t tf0, tm0, ts0;
       launch_order_coords(vp, blockIdx.x, tf0, tm0, ts0);
@@ -960,7 +1095,14 @@ k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const P
       __syncthreads();
     }
     int status = TILE_EMPTY;
-    if (!region_uniform(S)) status = tile_body<L, CO, MODE>(vp, o, S, tile, tf, tm, ts, 0, TS);
+    L first, second;
+    if (!region_uniform(S, S.lab + (vp.pad ? 16 / (int)sizeof(L) - 1 : 0), first, second)) {
+#if ZM_K2_PATH
+      status = tile_body<L, CO, MODE, true>(vp, o, S, tile, tf, tm, ts, 0, TS, first, second);
+      if (status == TILE_NOT_K2)
+#endif
+        status = tile_body<L, CO, MODE>(vp, o, S, tile, tf, tm, ts, 0, TS);
+    }
     if (status == TILE_EMPTY) zero_rows(vp, o, tf, tm, ts, 0, TS);
   } else {
     const uint32_t n = o.ctl->dense_count;  // written by the MODE 0 launch that precedes this one
