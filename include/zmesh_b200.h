@@ -47,6 +47,12 @@ void zm_destroy(zm_handle* h);
  * torch.cuda.current_stream().cuda_stream) instead of the handle's own; NULL restores the own one. */
 int zm_set_stream(zm_handle* h, void* cuda_stream);
 
+/* Order the handle's next work after everything queued so far on `producer_stream` (cudaStream_t as void*;
+ * NULL or 1 = the legacy default stream, 2 = the per-thread default stream, as in __cuda_array_interface__ v3):
+ * call before zm_mesh(..., ZM_MEM_DEVICE) when the label volume was written by kernels on another stream.  The
+ * reference has no counterpart (its input is host memory it reads synchronously, cMesher.hpp:29-36). */
+int zm_wait_stream(zm_handle* h, void* producer_stream);
+
 /* Replaces the resolution captured by `MesherClass(self.voxel_res)` in Mesher.mesh
  * (zmesh/_zmesh.pyx:494): call before zm_mesh to re-capture. */
 int zm_set_resolution(zm_handle* h, const float resolution[3]);

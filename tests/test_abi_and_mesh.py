@@ -136,8 +136,8 @@ def test_fanc_fixture_shape():
 
 
 def test_get_slices_the_staged_block():
-  """Host logic of Mesher.get (no GPU, no library): per-label views of the one bulk transfer, a private copy
-  when a label is asked for twice, float64 normals, empty meshes for missing / erased / face-less labels."""
+  """Host logic of Mesher.get (no GPU, no library): per-label views of the one bulk transfer, a fresh read from
+  the device when a label is asked for twice, float64 normals, empty meshes for missing / erased / face-less labels."""
   from zmesh_b200 import mesher as M
   m = M.Mesher.__new__(M.Mesher)
   m._voxel_res = np.array((4, 4, 40), dtype=np.float32)
@@ -149,11 +149,30 @@ def test_get_slices_the_staged_block():
   st.n = np.ones((10, 3), dtype=np.float32)
   st.index, st.given = {5: (0, 6, 0, 3), 9: (6, 10, 3, 4), 11: (10, 10, 4, 4)}, set()
   m._stage = st
-  a, b = m.get(5, normals=True), m.get(5, normals=True)
+  pristine_v, pristine_f = st.v.copy(), st.f.copy()
+  fetched = []
+
+  def fake_fetch(label, normals, voxel_centered, transpose):  # stands in for the per-label device read (zm_get)
+    fetched.append((label, normals, voxel_centered, transpose))
+    r = st.index[label]
+    out = Mesh(pristine_v[r[0]:r[1]].copy(), pristine_f[r[2]:r[3]].copy(), None)
+    out.normals = np.ones((r[1] - r[0], 3), dtype=np.float64) if normals else None
+    out.id = label
+    return out
+  m._fetch = fake_fetch
+  a = m.get(5, normals=True)
   assert isinstance(a, Mesh) and a.id == 5 and len(a) == 6 and a.faces.shape == (3, 3)
   assert a.vertices.dtype == np.float32 and a.faces.dtype == np.uint32
   assert a.normals.dtype == np.float64 and a.normals.shape == (6, 3)
-  assert a == b and np.shares_memory(a.vertices, st.v) and not np.shares_memory(a.vertices, b.vertices)
+  assert np.shares_memory(a.vertices, st.v) and not fetched
+  # the caller owns the first result: an in-place edit must not leak into a later get() of the same label,
+  # which is read back from the device (mesh.vertices += offset corrupted every later get)
+  a.vertices += 100.0
+  b = m.get(5, normals=True)
+  assert fetched == [(5, True, False, False)]
+  assert np.array_equal(b.vertices, pristine_v[0:6]) and not np.shares_memory(a.vertices, b.vertices)
+  a.vertices -= 100.0
+  assert a == b
   c = m.get(9)
   assert c.normals is None and c.id == 9 and np.array_equal(c.vertices, st.v[6:10]) and np.array_equal(c.faces, st.f[3:4])
   for missing in (11, 12345):

@@ -67,6 +67,7 @@ SYMBOLS = {
   "zm_destroy": (None, [C.c_void_p]),
   "zm_set_resolution": (C.c_int, [C.c_void_p, _f3]),
   "zm_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+  "zm_wait_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
   "zm_synth_voronoi": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p, _u64p, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]),
   "zm_mesh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]),
   "zm_mesh_slab": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(zm_slab)]),

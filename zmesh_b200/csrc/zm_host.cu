@@ -87,6 +87,7 @@ struct zm_handle {
 
   // results (host)
   bool has_result = false;
+  bool failed = false;  // the last zm_mesh returned an error: results are undefined until the next one succeeds
   uint64_t Vtot = 0, Ttot = 0;
   std::vector<LabelRec> recs;                   // storage (table) order
   std::unordered_map<uint64_t, uint32_t> index;  // label -> recs index
@@ -274,8 +275,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   ZM_CUDA(h, cudaSetDevice(h->device));
   h->stats = zm_stats_t{};
   h->stats.n_voxels = sx * sy * sz;
-  h->has_result = true;
-  if (sx == 0 || sy == 0 || sz == 0) return ZM_OK;
+  if (sx == 0 || sy == 0 || sz == 0) { h->has_result = true; return ZM_OK; }
   if (!labels) return fail(h, ZM_ERR_INVALID, "labels is NULL");
 
   VolParams vp{};
@@ -300,13 +300,14 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
     if (c_order) vp.ox = (uint32_t)slab->cube_lo; else vp.oz = (uint32_t)slab->cube_lo;
   }
   // no cube without two voxels along every axis (marching_cubes.hpp:226-257 loops are empty)
-  if (vp.Ef < 2 || vp.Em < 2 || vp.Es < 2) return ZM_OK;
+  if (vp.Ef < 2 || vp.Em < 2 || vp.Es < 2) { h->has_result = true; return ZM_OK; }
   vp.ntf = (vp.Ef + TF - 1) / TF; vp.ntm = (vp.Em + TM - 1) / TM; vp.nts = (vp.Es_own + TS - 1) / TS;
   vp.Efp = vp.ntf * TF;
   if (slab && 4ull * vp.Em * vp.Efp >= (1ull << 32))
     return fail(h, ZM_ERR_UNSUPPORTED, "slab plane too large for 32-bit boundary-slot indices (Em * Efp >= 2^30)");
   const unsigned long long ntiles = (unsigned long long)vp.ntf * vp.ntm * vp.nts;
-  if (ntiles > 0x7FFFFFFFull) return fail(h, ZM_ERR_UNSUPPORTED, "too many tiles for one launch; shard the volume");
+  if (ntiles > 0x7FFFFFFFull || vp.nts > 65535u || (vp.ntm + TM_GROUP - 1) / TM_GROUP > 65535u)
+    return fail(h, ZM_ERR_UNSUPPORTED, "too many tiles for one launch; shard the volume");
   const unsigned long long nvox = (unsigned long long)vp.nf * vp.nm * vp.ns;
   const size_t vol_bytes = (size_t)nvox * label_bytes;
 
@@ -360,7 +361,9 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
     Pass1Args p1{ht, d_ctl, h->d_rowinfo.as<uint32_t>(), h->d_perm.as<uint32_t>(),
                  h->d_vinfo.as<uint32_t>(), h->d_rec.as<u64>(), h->d_tl.as<TLEntry>(), h->d_hdr.as<TileHdr>(),
                  h->d_dense.as<uint32_t>(), capV, capR, capL};
-    ks.classify[0]<<<(uint32_t)ntiles, NT, ks.smem[0], st>>>(vp, tmap, p1);
+    // launch order = grid order (x fastest): f, row inside a group of TM_GROUP tile rows, then all s layers, then the next group
+    const dim3 grid0(vp.ntf * std::min<uint32_t>(TM_GROUP, vp.ntm), vp.nts, (vp.ntm + TM_GROUP - 1) / TM_GROUP);
+    ks.classify[0]<<<grid0, NT, ks.smem[0], st>>>(vp, tmap, p1);
     ZM_CUDA(h, cudaGetLastError());
     const uint32_t dense_grid = (uint32_t)std::min<unsigned long long>(ntiles, 148ull);
     ks.classify[1]<<<dense_grid, NT, ks.smem[1], st>>>(vp, tmap, p1);
@@ -440,6 +443,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   h->n_work = ctl.work_count;
   h->capL = capL;
 
+  h->has_result = true;
   h->stats.n_labels = h->sorted_ids.size();
   h->stats.n_vertices = Vtot;
   h->stats.n_faces = Ttot;
@@ -487,7 +491,7 @@ Pass2Args pass2_args(zm_handle* h) {
 // Pass 2 (lazy): faces once per zm_mesh; vertices per (voxel_centered, transpose, offset); normals per
 // transpose.  Everything is written in its final layout on the device.
 int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, const float* off) {
-  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  if (h->failed) return fail(h, ZM_ERR_STATE, "the last zm_mesh failed; mesh again before reading results");
   float o[3] = {h->res[0], h->res[1], h->res[2]};
   if (off) { o[0] = off[0]; o[1] = off[1]; o[2] = off[2]; }
   normals = normals ? 1 : 0; voxel_centered = voxel_centered ? 1 : 0; transpose = transpose ? 1 : 0;
@@ -642,6 +646,17 @@ int zm_set_stream(zm_handle* h, void* cuda_stream) {
   return ZM_OK;
 }
 
+int zm_wait_stream(zm_handle* h, void* producer_stream) {
+  if (!h) return ZM_ERR_INVALID;
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t ps = producer_stream ? static_cast<cudaStream_t>(producer_stream) : cudaStreamLegacy;
+  if (ps == h->stream) return ZM_OK;
+  // ev[0] is re-recorded by the next zm_mesh; a stream wait keeps the state it saw when it was queued
+  ZM_CUDA(h, cudaEventRecord(h->ev[0], ps));
+  ZM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev[0], 0));
+  return ZM_OK;
+}
+
 int zm_synth_voronoi(void* dst, int label_bytes, const uint64_t shape[3], const uint64_t origin[3],
                      const uint64_t full_shape[3], uint32_t pitch, uint64_t seed, int c_order, void* cuda_stream) {
   if (!dst || !shape || !origin || !full_shape || pitch == 0) return ZM_ERR_INVALID;
@@ -675,13 +690,17 @@ int zm_set_resolution(zm_handle* h, const float resolution[3]) {
 
 int zm_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz,
             int c_order, int close, int mem_kind) {
-  return run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, nullptr);
+  const int rc = run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, nullptr);
+  if (h) h->failed = rc != ZM_OK;
+  return rc;
 }
 
 int zm_mesh_slab(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz,
                  int c_order, int close, int mem_kind, const zm_slab* slab) {
   if (!slab) return ZM_ERR_INVALID;
-  return run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, slab);
+  const int rc = run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, slab);
+  if (h) h->failed = rc != ZM_OK;
+  return rc;
 }
 
 int zm_directory(zm_handle* h, uint64_t* labels, uint64_t* n_vertices, uint64_t* n_faces, uint64_t capacity) {
@@ -790,7 +809,9 @@ int zm_ids(zm_handle* h, uint64_t* out, uint64_t capacity) {
 int zm_get_counts(zm_handle* h, uint64_t label, uint64_t* nv, uint64_t* nf) {
   if (!h || !nv || !nf) return ZM_ERR_INVALID;
   *nv = *nf = 0;
-  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  // (before the first zm_mesh the handle answers like an empty volume: the reference's Mesher.__init__ builds an
+  // empty Mesher6464, zmesh/_zmesh.pyx:442-444)
+  if (h->failed) return fail(h, ZM_ERR_STATE, "the last zm_mesh failed; mesh again before reading results");
   auto it = h->index.find(label);
   if (it == h->index.end() || h->recs[it->second].erased) return ZM_OK;
   *nv = h->recs[it->second].nv;
@@ -801,7 +822,7 @@ int zm_get_counts(zm_handle* h, uint64_t label, uint64_t* nv, uint64_t* nf) {
 int zm_get(zm_handle* h, uint64_t label, int normals, int voxel_centered, int transpose,
            const float centering_offset[3], float* vertices, uint32_t* faces, float* normals_out) {
   if (!h) return ZM_ERR_INVALID;
-  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  if (h->failed) return fail(h, ZM_ERR_STATE, "the last zm_mesh failed; mesh again before reading results");
   auto it = h->index.find(label);
   if (it == h->index.end() || h->recs[it->second].erased) return ZM_OK;  // empty mesh
   const LabelRec& r = h->recs[it->second];

@@ -357,22 +357,11 @@ __device__ __forceinline__ void stage_origin(const VolParams& vp, uint32_t tf, u
   c2 = (int)(ts * TS) + vp.s_shift;
 }
 
-// Launch order of the MODE 0 tiles: f fastest, then a group of TM_GROUP tile rows, then ALL s layers, then
-// the next group.  The halo plane a tile shares with its s-neighbour is then re-read ntf * TM_GROUP tiles
+// Launch order of the MODE 0 tiles (a 3-d grid: x = tf + ntf * row-in-group, y = ts, z = group): f fastest, then a
+// group of TM_GROUP tile rows, then ALL s layers, then the next group.  The halo plane a tile shares with its s-neighbour is then re-read ntf * TM_GROUP tiles
 // later (8 MB of labels for c5) instead of ntf * ntm tiles later (268 MB > L2): ncu measured 12.6 % more
 // DRAM reads than the volume with the plain order.
 constexpr uint32_t TM_GROUP = 8;
-__device__ __forceinline__ void launch_order_coords(const VolParams& vp, uint32_t lin, uint32_t& tf, uint32_t& tm, uint32_t& ts) {
-  const uint32_t per_group = vp.ntf * TM_GROUP * vp.nts;
-  const uint32_t g = lin / per_group;
-  uint32_t rem = lin - g * per_group;
-  const uint32_t rows = min(TM_GROUP, vp.ntm - g * TM_GROUP);  // the last group may be short
-  tf = rem % vp.ntf;
-  rem /= vp.ntf;
-  tm = g * TM_GROUP + rem % rows;
-  ts = rem / rows;
-}
-
 // thread 0: publish the coordinates of a tile and (TMA path) start the load of its region
 template <typename L, int MODE>
 __device__ __forceinline__ void begin_tile(const VolParams& vp, const CUtensorMap* tmap, P1Smem<L, MODE>& S, uint32_t tf,
@@ -407,12 +396,11 @@ __device__ __forceinline__ void stage_plain(const VolParams& vp, P1Smem<L, MODE>
 }
 
 // true iff every staged element equals the first element of the region (then no cube of the tile is active and
-// no voxel owns a slot); 16-byte compares, one barrier.  On a non-uniform region every thread that met a different
-// element publishes one such label in S.recbase (any one writer wins): the second label of the two-label path.
+// no voxel owns a slot); 16-byte compares (loads issued back to back), one barrier
 template <typename L, int MODE>
-__device__ __forceinline__ bool region_uniform(P1Smem<L, MODE>& S, const L* lab, L& first, L& second) {
+__device__ __forceinline__ bool region_uniform(const P1Smem<L, MODE>& S, const L* lab, L& first) {
   constexpr int NQ = (int)sizeof(L) * RS * RM * P1Smem<L, MODE>::RFP / 16;
-  constexpr int PER = 16 / (int)sizeof(L);
+  constexpr int PASSES = (NQ + NT - 1) / NT;
   const uint4* q = reinterpret_cast<const uint4*>(S.lab);
   first = lab[0];
   uint4 ref;
@@ -425,26 +413,16 @@ __device__ __forceinline__ bool region_uniform(P1Smem<L, MODE>& S, const L* lab,
     if (sizeof(L) == 1) r = __byte_perm(r, r, 0x0000);
     ref = make_uint4(r, r, r, r);
   }
-  uint32_t acc = 0;
-  int at = 0;
-  for (int i = threadIdx.x; i < NQ; i += NT) {
-    const uint4 v = q[i];
-    const uint32_t d = (v.x ^ ref.x) | (v.y ^ ref.y) | (v.z ^ ref.z) | (v.w ^ ref.w);
-    acc |= d;
-    if (d) at = i;
-  }
-#if ZM_K2_PATH
-  if (MODE == 0 && acc) {
-    const L* e = S.lab + at * PER;
-    L other = e[0];
+  uint4 v[PASSES];
 #pragma unroll
-    for (int j = 1; j < PER; ++j) other = (other == first) ? e[j] : other;
-    S.recbase = (u64)other;
+  for (int j = 0; j < PASSES; ++j) {
+    const int i = threadIdx.x + j * NT;
+    v[j] = (j < NQ / NT || i < NQ) ? q[i] : ref;
   }
-#endif
-  const bool uni = __syncthreads_and(acc == 0u) != 0;
-  second = (L)S.recbase;
-  return uni;
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < PASSES; ++j) acc |= (v[j].x ^ ref.x) | (v[j].y ^ ref.y) | (v[j].z ^ ref.z) | (v[j].w ^ ref.w);
+  return __syncthreads_and(acc == 0u) != 0;
 }
 
 // all-zero rowinfo for the row segments of planes [h0, h0 + nh) of a tile without slots
@@ -561,47 +539,74 @@ __device__ __forceinline__ void edge_rows(P1Smem<L, MODE>& S, const L* lab) {
   }
 }
 
-// Two-label path, S1: the staged region holds (at most) the labels A and B, so ONE 33-bit mask per staged row
+template <typename L> __device__ __forceinline__ L shfl_label(L v, int src) {
+  if (sizeof(L) == 8) return (L)__shfl_sync(0xffffffffu, (u64)v, src);
+  return (L)__shfl_sync(0xffffffffu, (uint32_t)v, src);
+}
+
+// Two-label path, S1: if the staged region holds (at most) two labels A and B, ONE 33-bit mask per staged row
 // -- bit f = (voxel f carries A) -- says everything: edges are where the mask changes, the non-zero masks follow
 // from which of A / B is the background.  One compare pair + one ballot per row instead of edge_rows' three label
-// compares + five ballots per voxel.  Returns true when a voxel outside {A, B} was met (the tile then takes the
-// general path).  The masks live in S.lkeys[2 ..] (64-bit, bit 32 = the +f halo column); lkeys[0 / 1] hold A / B.
+// compares + five ballots per voxel.  A is the region's first label; every warp discovers the other label of ITS
+// rows on the way (the first voxel that is not A) and checks its rows against it; the candidates of the warps are
+// compared after the barrier (k2_second_label).  Returns true when the warp met a third label (the tile then takes
+// the general path).  The masks live in S.lkeys[2 ..] (64-bit, bit 32 = the +f halo column), the candidates in rstage.
 constexpr int K2_MASK0 = 2;  // first lkeys entry used for the row masks
 template <typename L, int MODE>
-__device__ __forceinline__ bool k2_rows(P1Smem<L, MODE>& S, const L* lab, const L A, const L B) {
+__device__ __forceinline__ bool k2_rows(P1Smem<L, MODE>& S, const L* lab, const L A) {
   constexpr int RFP = P1Smem<L, MODE>::RFP;
   constexpr uint32_t FULL = 0xffffffffu;
   static_assert(Caps<MODE>::LT >= K2_MASK0 + RS * RM, "row masks overlay the label keys");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t* const mw = reinterpret_cast<uint32_t*>(S.lkeys + K2_MASK0);
-  bool bad = false;
-#pragma unroll 3
-  for (int r = warp; r < RS * RM; r += NW) {
-    const L a = lab[r * RFP + lane];
+  constexpr int NR = RS * RM, PASSES = (NR + NW - 1) / NW;
+  static_assert(PASSES <= 32, "one lane per row of the warp for the halo column");
+  bool bad = false, hasB = false;
+  L B = A;  // (until the warp meets another label)
+#pragma unroll
+  for (int j = 0; j <= PASSES; ++j) {
+    // passes 0 .. PASSES-1: lane f of row warp + j * NW; the last pass: the +f halo column of the warp's rows
+    const int r = j < PASSES ? warp + j * NW : warp + lane * NW;
+    const bool in = j < PASSES ? (j < NR / NW || r < NR) : (lane < PASSES && r < NR);
+    if (j < PASSES && !in) continue;  // (warp-uniform: only pass PASSES-1 is partial)
+    const L a = in ? lab[r * RFP + (j < PASSES ? lane : TF)] : A;
     const bool pa = a == A;
-    bad |= !(pa || a == B);
     const uint32_t m = __ballot_sync(FULL, pa);
-    if (lane == 0) mw[2 * r] = m;
+    if (m != FULL && !hasB) {  // (warp-uniform) the warp's second label
+      B = shfl_label<L>(a, __ffs(~m) - 1);
+      hasB = true;
+    }
+    bad = bad || !(pa || a == B);
+    if (j < PASSES) {
+      if (lane == 0) mw[2 * r] = m;
+    } else if (in) {
+      mw[2 * r + 1] = pa ? 1u : 0u;
+    }
   }
-  if (threadIdx.x < RS * RM) {  // the +f halo column
-    const L a = lab[threadIdx.x * RFP + TF];
-    const bool pa = a == A;
-    bad |= !(pa || a == B);
-    mw[2 * threadIdx.x + 1] = pa ? 1u : 0u;
-  }
+  if (lane == 0) reinterpret_cast<u64*>(S.rstage)[warp] = (u64)B;  // == A: none met
   return bad;
+}
+
+// after the barrier that follows k2_rows: 0 = no label but A in the used columns (nothing to mesh), 1 = exactly one
+// other label (returned in B), 2 = the warps met different labels (general path)
+template <typename L, int MODE>
+__device__ __forceinline__ int k2_second_label(const P1Smem<L, MODE>& S, const L A, L& B) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const L c = (L)reinterpret_cast<const u64*>(S.rstage)[lane & (NW - 1)];
+  const uint32_t has = __ballot_sync(FULL, c != A);
+  if (has == 0u) return 0;
+  B = shfl_label<L>(c, __ffs(has) - 1);
+  return __any_sync(FULL, c != A && c != B) ? 2 : 1;
 }
 
 enum : int { TILE_EMPTY = 0, TILE_DEFERRED = 1, TILE_DONE = 2, TILE_NOT_K2 = 3 };
 
 // Everything after staging for planes [h0, h0 + nh) of a tile (all 8 in MODE 0).  The caller has
 // staged the region and synchronised; the per-tile tables are cleared here.
-template <typename L, bool CO, int MODE, bool K2 = false>
+template <typename L, bool CO, int MODE>
 __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o, P1Smem<L, MODE>& S, const uint32_t tile,
-                                         const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh,
-                                         const L keyA = 0, const L keyB = 0) {
-  static_assert(!K2 || (MODE == 0 && ZM_S1_ROWMASK && ZM_S2_TWOWARPS), "the two-label path is a MODE 0 / row-mask variant");
-  constexpr int LTU = K2 ? 2 : Caps<MODE>::LT;  // label-table entries in use
+                                         const uint32_t tf, const uint32_t tm, const uint32_t ts, const int h0, const int nh) {
   constexpr int RFP = P1Smem<L, MODE>::RFP;
   constexpr int LT = Caps<MODE>::LT, VCAP = TileCap<L, MODE>::V, RCAP = TileCap<L, MODE>::R, PROBES = Caps<MODE>::PROBES;
   constexpr uint32_t FULL = 0xffffffffu;
@@ -611,22 +616,14 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
   const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
   const L* const lab = S.lab + (vp.pad ? ALIGN - 1 : 0);
 
-  if (K2) {
-    if (tid < 2) { S.lkeys[tid] = (u64)(tid == 0 ? keyA : keyB); S.lcnt[tid] = 0u; }
-  } else {
-    for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
-  }
+  for (int i = tid; i < LT; i += NT) { S.lkeys[i] = 0ull; S.lcnt[i] = 0u; }
   if (tid == 0) { S.nrec = 0; S.overflow = 0; S.ci = 0; S.ttot = 0; }
 
 #if ZM_S1_ROWMASK
   // ---- S1 (row masks): phase A: edge / non-zero masks of all staged rows; phase B: lane j < TM of warp w turns
   //      them into the bit planes and the active-cube mask of row (w, j), then S2's in-row prefixes ----
-  if (K2) {
-    if (__syncthreads_or(k2_rows<L, MODE>(S, lab, keyA, keyB) ? 1 : 0)) return TILE_NOT_K2;
-  } else {
-    edge_rows<L, MODE>(S, lab);
-    __syncthreads();
-  }
+  edge_rows<L, MODE>(S, lab);
+  __syncthreads();
   bool any = false;
   uint32_t packed = 0;  // slots of the row | active voxels of the row << 16   (of the thread's row)
 #if ZM_S2_TWOWARPS
@@ -639,27 +636,12 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     const int row = pw * TM + pj;
     uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0, act = 0;
     if (pw >= h0 && pw < h0 + nh) {
-      uint4 q, qm, qs;  // Ef, Em, Es, Z of rows (m, s), (m + 1, s), (m, s + 1)
-      uint32_t zf, ef3;  // non-zero mask of the +f neighbours of (m, s); Ef of (m + 1, s + 1)
-      if (K2) {
-        const u64* mk = S.lkeys + K2_MASK0 + (pw * RM + pj);
-        const u64 m00 = mk[0], m10 = mk[1], m01 = mk[RM], m11 = mk[RM + 1];
-        const bool zA = keyA == 0, zB = keyB == 0;  // (at most one of the two is the background)
-        auto nz = [&](uint32_t isA) { return zA ? ~isA : (zB ? isA : 0xffffffffu); };
-        q.x = (uint32_t)(m00 ^ (m00 >> 1)); q.y = (uint32_t)(m00 ^ m10); q.z = (uint32_t)(m00 ^ m01); q.w = nz((uint32_t)m00);
-        zf = nz((uint32_t)(m00 >> 1));
-        qm.x = (uint32_t)(m10 ^ (m10 >> 1)); qm.w = nz((uint32_t)m10);
-        qs.x = (uint32_t)(m01 ^ (m01 >> 1)); qs.y = (uint32_t)(m01 ^ m11); qs.w = nz((uint32_t)m01);
-        qm.y = qm.z = qs.z = 0u;
-        ef3 = (uint32_t)(m11 ^ (m11 >> 1));
-      } else {
-        const uint32_t* e0 = S.vstage + (pw * RM + pj) * EM_WORDS;
-        q = *reinterpret_cast<const uint4*>(e0);
-        zf = e0[4];
-        qm = *reinterpret_cast<const uint4*>(e0 + EM_WORDS);
-        qs = *reinterpret_cast<const uint4*>(e0 + RM * EM_WORDS);
-        ef3 = e0[(RM + 1) * EM_WORDS];
-      }
+      const uint32_t* e0 = S.vstage + (pw * RM + pj) * EM_WORDS;
+      const uint4 q = *reinterpret_cast<const uint4*>(e0);                     // Ef, Em, Es, Z of (m, s)
+      const uint32_t zf = e0[4];
+      const uint4 qm = *reinterpret_cast<const uint4*>(e0 + EM_WORDS);         // (m + 1, s)
+      const uint4 qs = *reinterpret_cast<const uint4*>(e0 + RM * EM_WORDS);    // (m, s + 1)
+      const uint32_t ef3 = e0[(RM + 1) * EM_WORDS];                            // Ef of (m + 1, s + 1)
       const uint32_t nonuni = q.x | qm.x | qs.x | ef3 | q.y | qs.y | q.z;     // cube has two different corners
       uint32_t pf = q.x, pm = q.y, ps = q.z, cube = nonuni;
       if (!(ef0 + TF + 1 <= vp.Ef && em0 + TM + 1 <= vp.Em && es0 + TS + 1 <= vp.Es)) {
@@ -790,61 +772,6 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     const uint32_t row = vidx >> 5;
     const uint32_t ltf = (1u << lf) - 1u;
     const uint32_t rowpre = S.pl[row][6];
-    if constexpr (K2) {
-      // corner mask of label A straight from the four row masks; B's is the complement.  Every lane of the warp
-      // works on the same label, so its counter is the only address the shared atomic sees.
-      const u64* mk = S.lkeys + K2_MASK0 + (ls * RM + lm);
-      uint32_t b[4];  // index dm + 2 * ds: bits (f, f + 1) of the row
-      b[0] = (uint32_t)(mk[0] >> lf) & 3u; b[1] = (uint32_t)(mk[1] >> lf) & 3u;
-      b[2] = (uint32_t)(mk[RM] >> lf) & 3u; b[3] = (uint32_t)(mk[RM + 1] >> lf) & 3u;
-      uint32_t mskA = 0;
-#pragma unroll
-      for (int n = 0; n < 8; ++n) mskA |= ((b[corner_dm<CO>(n) + 2 * corner_ds<CO>(n)] >> corner_df<CO>(n)) & 1u) << n;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if ((k == 0 ? keyA : keyB) == 0) continue;  // the background is never meshed (uniform branch)
-        const uint32_t msk = k == 0 ? mskA : (~mskA & 0xFFu);
-        const uint32_t cs = ~msk & 0xFFu;
-        uint32_t nt = 0, mine = 0;
-        if (valid) {
-          if (cube) nt = __ldg(&TRI_COUNT_D[cs]);
-          const uint32_t nb = ((msk >> corner_plus_f<CO>()) & 1u) | (((msk >> corner_plus_m<CO>()) & 1u) << 2) |
-                              (((msk >> corner_plus_s<CO>()) & 1u) << 4);
-          mine = ((msk & 1u) ? (0x15u & ~nb) : (nb << 1)) & amask;
-        }
-        const uint32_t nv = __popc(mine);
-        const bool work = (nv | nt) != 0u;
-        uint32_t old = 0;
-        if (work) old = atomicAdd(&S.lcnt[k], nv | (nt << 16));
-        if (nv) {
-          uint32_t r = old & 0xFFFFu;
-          uint32_t mm = mine;
-          while (mm) {
-            const int s6 = __ffs(mm) - 1;
-            mm &= mm - 1u;
-            const uint32_t lg = rowpre + S.pp8[row][s6] + __popc(S.pl[row][s6] & ltf);
-            S.vstage[lg] = r | ((uint32_t)k << 11) | (vidx << 18) | ((uint32_t)s6 << 29);
-            ++r;
-          }
-        }
-        const bool hasrec = nt != 0u;
-        const uint32_t rb = __ballot_sync(FULL, hasrec);
-        if (rb) {
-          uint32_t rbase = 0;
-          if (lane == 0) rbase = atomicAdd(&S.nrec, (uint32_t)__popc(rb));
-          rbase = __shfl_sync(FULL, rbase, 0);
-          if (hasrec) {
-            const uint32_t pos = rbase + __popc(rb & ltm);
-            if (pos < (uint32_t)RCAP) {
-              S.rstage[pos] = vidx | (cs << 11) | ((uint32_t)k << 19);
-              S.rtoff[pos] = (uint16_t)(old >> 16);
-            } else {
-              S.overflow = 1u;
-            }
-          }
-        }
-      }
-    } else {
     L c[8];
 #pragma unroll
     for (int n = 0; n < 8; ++n)
@@ -949,7 +876,6 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
         }
       }
     }
-    }  // (general path)
   }
   __syncthreads();  // the staged labels are dead from here on (lvb / cidx reuse their memory)
   if (S.overflow) {
@@ -972,9 +898,8 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     S.recbase = recbase;
     S.ok1 = ok ? 1u : 0u;
   }
-  for (int i = tid; i < LTU; i += NT) {
-    u64 label = S.lkeys[i];
-    if (K2 && label != 0ull && S.lcnt[i] == 0u) S.lkeys[i] = label = 0ull;  // (present in the region, nothing to mesh here)
+  for (int i = tid; i < LT; i += NT) {
+    const u64 label = S.lkeys[i];
     if (label != 0ull) {
       const uint32_t cnt = S.lcnt[i];
       const uint32_t nv = cnt & 0xFFFFu, nt = cnt >> 16;
@@ -1045,7 +970,7 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
   __syncthreads();
   if (!S.ok2) return TILE_DONE;
   const uint32_t tlbase = S.tlbase;
-  for (int i = tid; i < LTU; i += NT) {
+  for (int i = tid; i < LT; i += NT) {
     if (S.lkeys[i] != 0ull) {
       TLEntry e;
       e.a = S.tla[i];
@@ -1056,12 +981,276 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
   return TILE_DONE;
 }
 
+// ---------------------------------------------------------------------------------------------
+// The two-label path of MODE 0 (ZM_K2_PATH): the staged region holds exactly two labels A and B (one of them may
+// be the background).  82 % of c5's non-empty tiles and a third of connectomics' are of this kind.
+//   * S1: one 33-bit mask per staged row (k2_rows); edges, non-zero masks, slot planes and per-row counts of A's
+//     slots are bit arithmetic on whole rows; B's corner mask of a cube is the complement of A's.
+//   * every count the global reservations need is known after the row scan (slots, A's slots, the non-uniform
+//     cubes = records per label), so the cursor and label-table atomics are ISSUED before the active voxels are
+//     compacted and their results are picked up after S3: their L2 round trips (7 % of the kernel's warp time on
+//     the critical path of the general formulation) overlap the compaction and S3.
+//   * S3 splits the (chunk of 32 active voxels, label) pairs over the warps: all lanes of a warp work on the same
+//     label, whose counter is the one address the shared-memory atomic ranks them on.
+template <typename L, bool CO>
+__device__ __forceinline__ int tile_body_k2(const VolParams& vp, const Pass1Args& o, P1Smem<L, 0>& S, const uint32_t tile,
+                                            const uint32_t tf, const uint32_t tm, const uint32_t ts, const L keyA) {
+  constexpr int VCAP = TileCap<L, 0>::V, RCAP = TileCap<L, 0>::R;
+  constexpr uint32_t FULL = 0xffffffffu;
+  constexpr int ALIGN = 16 / (int)sizeof(L);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ltm = (1u << lane) - 1u;
+  const uint32_t ef0 = tf * TF, em0 = tm * TM, es0 = ts * TS;
+  const L* const lab = S.lab + (vp.pad ? ALIGN - 1 : 0);
+
+  if (tid < 2) S.lcnt[tid] = 0u;
+  if (tid == 0) S.nrec = 0;
+  if (__syncthreads_or(k2_rows<L, 0>(S, lab, keyA) ? 1 : 0)) return TILE_NOT_K2;
+  L keyB = keyA;
+  {
+    const int n2 = k2_second_label<L, 0>(S, keyA, keyB);
+    if (n2 == 0) return TILE_EMPTY;
+    if (n2 == 2) return TILE_NOT_K2;
+  }
+  const bool zA = keyA == 0, zB = keyB == 0;  // (at most one of the two is the background)
+
+  // ---- phase B + S2: thread t < 64 owns row t (plane pw, row pj) ----
+  bool any = false;
+  uint32_t packed = 0;   // slots of the row | active voxels of the row << 16
+  uint32_t packed2 = 0;  // slots of the row that belong to A | non-uniform (valid) cubes of the row << 16
+  const int pw = tid >> 3, pj = tid & 7;
+  if (warp < NROWS / 32) {
+    const int row = tid;
+    const u64* mk = S.lkeys + K2_MASK0 + (pw * RM + pj);
+    const u64 m00 = mk[0], m10 = mk[1], m01 = mk[RM], m11 = mk[RM + 1];
+    const uint32_t a00 = (uint32_t)m00, a00f = (uint32_t)(m00 >> 1), a10 = (uint32_t)m10, a01 = (uint32_t)m01;
+    const uint32_t ef = a00 ^ a00f, em = a00 ^ a10, es = a00 ^ a01;
+    const uint32_t nonuni = ef | em | es | (uint32_t)(m10 ^ (m10 >> 1)) | (uint32_t)(m01 ^ (m01 >> 1)) |
+                            (uint32_t)(m11 ^ (m11 >> 1)) | (uint32_t)(m01 ^ m11);
+    uint32_t pf = ef, pm = em, ps = es, cube = nonuni;
+    if (!(ef0 + TF + 1 <= vp.Ef && em0 + TM + 1 <= vp.Em && es0 + TS + 1 <= vp.Es)) {
+      // volume boundary within reach (see tile_body): slots need their upper voxel inside the extended volume and
+      // a lower voxel this shard owns; a cube needs all three upper neighbours
+      const uint32_t nfv = vp.Ef - ef0;
+      const uint32_t VF = nfv >= 32u ? FULL : (1u << nfv) - 1u;
+      const uint32_t NF1 = nfv >= 33u ? FULL : (1u << (nfv - 1u)) - 1u;
+      const uint32_t em_ = em0 + (uint32_t)pj, es_ = es0 + (uint32_t)pw;
+      const bool rowok = em_ < vp.Em && es_ < vp.Es_own;
+      const bool nm1 = em_ + 1 < vp.Em, ns1 = es_ + 1 < vp.Es;
+      pf = rowok ? pf & NF1 : 0u;
+      pm = rowok && nm1 ? pm & VF : 0u;
+      ps = rowok && ns1 ? ps & VF : 0u;
+      cube = rowok && nm1 && ns1 ? nonuni & NF1 : 0u;
+    }
+    // slot 2d: the edge's lower voxel carries a label (A where its mask bit is set, else B); 2d + 1: the upper one
+    const uint32_t nzlo = zA ? ~a00 : (zB ? a00 : FULL);  // lower voxel is not the background
+    const uint32_t b0 = pf & nzlo, b2 = pm & nzlo, b4 = ps & nzlo;
+    const uint32_t b1 = pf & (zA ? ~a00f : (zB ? a00f : FULL));
+    const uint32_t b3 = pm & (zA ? ~a10 : (zB ? a10 : FULL));
+    const uint32_t b5 = ps & (zA ? ~a01 : (zB ? a01 : FULL));
+    const uint32_t act = b0 | b1 | b2 | b3 | b4 | b5 | cube;
+    *reinterpret_cast<uint4*>(&S.pl[row][0]) = make_uint4(b0, b1, b2, b3);
+    *reinterpret_cast<uint4*>(&S.pl[row][4]) = make_uint4(b4, b5, 0u, act);
+    any = act != 0u;
+    const uint32_t c0 = __popc(b0), c1 = c0 + __popc(b1), c2 = c1 + __popc(b2), c3 = c2 + __popc(b3);
+    const uint32_t c4 = c3 + __popc(b4);
+    *reinterpret_cast<uint2*>(S.pp8[row]) = make_uint2((c0 << 8) | (c1 << 16) | (c2 << 24), c3 | (c4 << 8));
+    packed = (c4 + __popc(b5)) | ((uint32_t)__popc(act) << 16);
+    const uint32_t nva = __popc(b0 & a00) + __popc(b2 & a00) + __popc(b4 & a00) + __popc(b1 & a00f) + __popc(b3 & a10) +
+                         __popc(b5 & a01);
+    packed2 = nva | ((uint32_t)__popc(cube) << 16);
+    uint32_t rinc = packed;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(FULL, rinc, d);
+      if (lane >= d) rinc += t;
+    }
+    const uint32_t ex = rinc - packed;
+    S.pl[tid][6] = ex & 0xFFFFu;
+    S.actpre[tid] = (uint16_t)(ex >> 16);
+    const uint32_t tot2 = __reduce_add_sync(FULL, packed2);
+    if (lane == 31) { S.wtot[warp] = rinc; S.wtot[2 + warp] = tot2; }
+  }
+  if (!__syncthreads_or(any ? 1 : 0)) return TILE_EMPTY;
+  const uint32_t g0 = S.wtot[0];
+  const uint32_t nslots = (g0 + S.wtot[1]) & 0xFFFFu, nact = (g0 + S.wtot[1]) >> 16;
+  const uint32_t t2 = S.wtot[2] + S.wtot[3];
+  const uint32_t nvA = t2 & 0xFFFFu, ncubes = t2 >> 16;
+  const uint32_t nnz = (zA ? 0u : 1u) + (zB ? 0u : 1u);
+  const uint32_t nrec = ncubes * nnz;  // every non-uniform cube holds both labels
+  if (nslots > (uint32_t)VCAP || nrec > (uint32_t)RCAP) {
+    if (tid == 0) o.dense_list[atomicAdd(&o.ctl->dense_count, 1u)] = tile;
+    return TILE_DEFERRED;
+  }
+  if (warp == 1) S.pl[tid][6] += g0 & 0xFFFFu;
+  const uint32_t actbase = warp >= NW / 2 ? g0 >> 16 : 0u;
+  const bool hasA = !zA && (nvA | ncubes) != 0u, hasB = !zB && ((nslots - nvA) | ncubes) != 0u;
+  const uint32_t nlab = (hasA ? 1u : 0u) + (hasB ? 1u : 0u);
+
+  // ---- early reservations (results are read after S3) ----
+  u64 r_gbase = 0, r_recbase = 0, r_oldv = 0;
+  int r_gs = 0;
+  if (tid == 0) {
+    if (nslots) r_gbase = atomicAdd(&o.ctl->cur_perm, (u64)nslots);
+    if (nrec) r_recbase = atomicAdd(&o.ctl->cur_rec, (u64)nrec);
+  }
+  const bool lab_lane = warp == 1 && lane < 2 && (lane == 0 ? hasA : hasB);  // lane 0: A, lane 1: B
+  if (lab_lane) {
+    const int gs = gtab_insert(o.ht, (u64)(lane == 0 ? keyA : keyB), &o.ctl->flags);
+    r_gs = gs >= 0 ? gs : 0;
+    if (gs >= 0) r_oldv = atomicAdd(&o.ht.cnt[gs], (u64)(lane == 0 ? nvA : nslots - nvA));
+  }
+
+  // ---- compaction of the active voxels of the warp's own plane ----
+#pragma unroll
+  for (int j = 0; j < TM; ++j) {
+    const int row = warp * TM + j;
+    const uint32_t mask = S.pl[row][7];
+    if ((mask >> lane) & 1u) S.alist[actbase + S.actpre[row] + __popc(mask & ltm)] = (uint16_t)(row * TF + lane);
+  }
+  __syncthreads();
+
+  // ---- S3: (chunk of 32 active voxels, label) tasks over the warps ----
+  const uint32_t ntask = ((nact + 31u) >> 5) * nnz;
+  for (uint32_t t = warp; t < ntask; t += NW) {
+    const uint32_t k = nnz == 2u ? (t & 1u) : (zA ? 1u : 0u);
+    const uint32_t i = (nnz == 2u ? (t >> 1) : t) * 32u + lane;
+    const bool valid = i < nact;
+    const uint32_t vidx = valid ? S.alist[i] : 0u;
+    const int lf = vidx & 31, lm = (vidx >> 5) & 7, ls = vidx >> 8;
+    const bool axf = ef0 + lf + 1 < vp.Ef, axm = em0 + lm + 1 < vp.Em, axs = es0 + ls + 1 < vp.Es;
+    const uint32_t amask = (axf ? 0x03u : 0u) | (axm ? 0x0Cu : 0u) | (axs ? 0x30u : 0u);
+    const bool cube = axf && axm && axs;
+    const uint32_t row = vidx >> 5;
+    const uint32_t ltf = (1u << lf) - 1u;
+    const uint32_t rowpre = S.pl[row][6];
+    const u64* mk = S.lkeys + K2_MASK0 + (ls * RM + lm);
+    uint32_t b[4];  // index dm + 2 * ds: bits (f, f + 1) of the row
+    b[0] = (uint32_t)(mk[0] >> lf) & 3u; b[1] = (uint32_t)(mk[1] >> lf) & 3u;
+    b[2] = (uint32_t)(mk[RM] >> lf) & 3u; b[3] = (uint32_t)(mk[RM + 1] >> lf) & 3u;
+    uint32_t msk = 0;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) msk |= ((b[corner_dm<CO>(n) + 2 * corner_ds<CO>(n)] >> corner_df<CO>(n)) & 1u) << n;
+    if (k) msk = ~msk & 0xFFu;
+    const uint32_t cs = ~msk & 0xFFu;
+    uint32_t nt = 0, mine = 0;
+    if (valid) {
+      if (cube) nt = __ldg(&TRI_COUNT_D[cs]);
+      const uint32_t nb = ((msk >> corner_plus_f<CO>()) & 1u) | (((msk >> corner_plus_m<CO>()) & 1u) << 2) |
+                          (((msk >> corner_plus_s<CO>()) & 1u) << 4);
+      mine = ((msk & 1u) ? (0x15u & ~nb) : (nb << 1)) & amask;
+    }
+    const uint32_t nv = __popc(mine);
+    uint32_t old = 0;
+    if ((nv | nt) != 0u) old = atomicAdd(&S.lcnt[k], nv | (nt << 16));
+    if (nv) {
+      uint32_t r = old & 0xFFFFu;
+      uint32_t mm = mine;
+      while (mm) {
+        const int s6 = __ffs(mm) - 1;
+        mm &= mm - 1u;
+        const uint32_t lg = rowpre + S.pp8[row][s6] + __popc(S.pl[row][s6] & ltf);
+        S.vstage[lg] = r | (k << 11) | (vidx << 18) | ((uint32_t)s6 << 29);
+        ++r;
+      }
+    }
+    const bool hasrec = nt != 0u;
+    const uint32_t rb = __ballot_sync(FULL, hasrec);
+    if (rb) {
+      uint32_t rbase = 0;
+      if (lane == 0) rbase = atomicAdd(&S.nrec, (uint32_t)__popc(rb));
+      rbase = __shfl_sync(FULL, rbase, 0);
+      if (hasrec) {
+        const uint32_t pos = rbase + __popc(rb & ltm);  // (< nrec <= RCAP)
+        S.rstage[pos] = vidx | (cs << 11) | (k << 19);
+        S.rtoff[pos] = (uint16_t)(old >> 16);
+      }
+    }
+  }
+  __syncthreads();  // (the staged labels have been dead since k2_rows: lvb / cidx reuse their memory)
+
+  // ---- publish the early reservations, issue the remaining atomics ----
+  const uint32_t ntA = S.lcnt[0] >> 16, ntB = S.lcnt[1] >> 16;
+  u64 r_tl = 0, r_oldt = 0;
+  uint32_t r_wc = 0;
+  if (tid == 0) {
+    const bool ok = r_gbase + nslots <= o.capV && r_recbase + nrec <= o.capR;
+    if (!ok) atomicOr(&o.ctl->flags, FLAG_CAP);
+    if (S.nrec != nrec) atomicOr(&o.ctl->flags, FLAG_INTERNAL);
+    S.gbase = (uint32_t)r_gbase;
+    S.recbase = r_recbase;
+    S.ok1 = ok ? 1u : 0u;
+    if (nlab) r_tl = atomicAdd(&o.ctl->cur_tl, (u64)nlab);
+    if (ok) r_wc = atomicAdd(&o.ctl->work_count, 1u);
+    if (ntA + ntB) atomicAdd(&o.ctl->cur_tri, (u64)(ntA + ntB));
+  }
+  if (lab_lane) {
+    S.lvb[lane] = (uint32_t)r_oldv;
+    r_oldt = atomicAdd(&o.ht.cnt[r_gs], (u64)(lane == 0 ? ntA : ntB) << 32);
+  }
+  const uint32_t ciB = hasA ? 1u : 0u;  // tile-local label indices: A -> 0, B -> 1 (0 when A is not meshed here)
+  __syncthreads();
+  if (!S.ok1) return TILE_DONE;  // capacity guess too small: the cursors give the exact need; host reruns
+  const uint32_t gbase = S.gbase;
+  const u64 recbase = S.recbase;
+
+  // ---- S6: flush rowinfo, perm / vinfo and the records (coalesced) ----
+  {
+    const int row = tid >> 2, q = tid & 3;  // 4 threads per row segment, 8 bytes each
+    const uint32_t rs = ts * TS + row / TM, rm = tm * TM + row % TM;
+    if (rs < vp.Es_own && rm < vp.Em) {
+      uint2 w = *reinterpret_cast<const uint2*>(&S.pl[row][2 * q]);
+      if (q == 3) { w.x += gbase; w.y = 0u; }
+      reinterpret_cast<uint2*>(o.rowinfo + (((size_t)rs * vp.Em + rm) * vp.ntf + tf) * RI_WORDS)[q] = w;
+    }
+  }
+  const uint32_t lvbA = S.lvb[0], lvbB = S.lvb[1];
+  for (uint32_t i = tid; i < nslots; i += NT) {
+    const uint32_t w = S.vstage[i];
+    const bool isB = (w >> 11) & 1u;
+    o.perm[(size_t)gbase + i] = (isB ? lvbB : lvbA) + (w & 0x7FFu);
+    o.vinfo[(size_t)gbase + i] = (w >> 18) | ((isB ? ciB : 0u) << 14);
+  }
+  for (uint32_t i = tid; i < nrec; i += NT) {
+    const uint32_t w = S.rstage[i];
+    o.rec[recbase + i] = (u64)((w & 0x7FFFFu) | (((w >> 19) ? ciB : 0u) << 19)) | ((u64)S.rtoff[i] << 32);
+  }
+  if (tid == 0) {
+    const bool ok = r_tl + nlab <= o.capL;
+    if (!ok) atomicOr(&o.ctl->flags, FLAG_CAP);
+    else {
+      TileHdr h;
+      h.recbase = recbase;
+      h.gbase = gbase;
+      h.tlbase = (uint32_t)r_tl;
+      h.nslots = (uint16_t)nslots;
+      h.nrec = (uint16_t)nrec;
+      h.nlab = (uint16_t)nlab;
+      h.pad = 0;
+      h.tile = tile;
+      h.pad2 = 0;
+      o.hdr[r_wc] = h;
+    }
+    S.tlbase = (uint32_t)r_tl;
+    S.ok2 = ok ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!S.ok2) return TILE_DONE;
+  if (lab_lane) {
+    TLEntry e;
+    e.a = (u64)(uint32_t)r_gs | (r_oldt & 0xFFFFFFFF00000000ull);
+    e.b = 0;
+    o.tl[S.tlbase + (lane == 0 ? 0u : ciB)] = e;
+  }
+  return TILE_DONE;
+}
+
 // MODE 0: one CTA per tile (the hardware CTA scheduler overlaps the TMA wait of one tile with the
 // work of the others resident on the SM).  MODE 1: the queued dense tiles, two half tiles each.
-#ifndef ZM_PREFETCH_TILES
-#define ZM_PREFETCH_TILES (148 * 6)
+#ifndef ZM_PREFETCH_LAYERS
+#define ZM_PREFETCH_LAYERS 2
 #endif
-constexpr uint32_t PREFETCH_DISTANCE = ZM_PREFETCH_TILES;  // tiles ahead (in launch order) whose region is pulled into L2 (0: off)
+constexpr uint32_t PREFETCH_LAYERS = ZM_PREFETCH_LAYERS;  // s-layers ahead whose region is pulled into L2 (0: off); c5: 2 layers = 1024 CTAs
 template <typename L, bool CO, int MODE>
 __global__ void __launch_bounds__(NT, MODE == 0 ? (sizeof(L) == 8 ? ZM_U64_CTAS : ZM_U32_CTAS) : 1)
 k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const Pass1Args o) {
@@ -1072,21 +1261,23 @@ k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const P
     fence_mbar_init();
   }
   if constexpr (MODE == 0) {
-    if (tid == 0) {
-      uint32_t tf0, tm0, ts0;
-      launch_order_coords(vp, blockIdx.x, tf0, tm0, ts0);
-      begin_tile(vp, &tmap, S, tf0, tm0, ts0);
-      const uint32_t pt = blockIdx.x + PREFETCH_DISTANCE;
-      if (PREFETCH_DISTANCE != 0 && vp.use_tma && pt < vp.ntf * vp.ntm * vp.nts) {
-        uint32_t ptf, ptm, pts;
-        launch_order_coords(vp, pt, ptf, ptm, pts);
+    // 3-d grid in the launch order described at TM_GROUP: x = tf + ntf * (row inside the group), y = ts, z = group.
+    // Every thread derives the coordinates itself (one division by ntf), so nothing but the mbarrier initialisation
+    // precedes the first CTA barrier (the serial prologue of thread 0 used to cost 10 % of the kernel's warp time).
+    const uint32_t tmg = blockIdx.x / vp.ntf;
+    const uint32_t tf = blockIdx.x - tmg * vp.ntf, tm = blockIdx.z * TM_GROUP + tmg, ts = blockIdx.y;
+    if (tm >= vp.ntm) return;  // (the last group may be short)
+    if (tid == 0) begin_tile(vp, &tmap, S, tf, tm, ts);
+    __syncthreads();  // mbarrier initialised
+    if (tid == 0 && PREFETCH_LAYERS != 0 && vp.use_tma) {
+      // pull the region of the tile PREFETCH_LAYERS s-layers up (launched ntf * TM_GROUP * PREFETCH_LAYERS CTAs later) into L2
+      const uint32_t pts = ts + PREFETCH_LAYERS;
+      if (pts < vp.nts) {
         int c0, c1, c2;
-        stage_origin<L>(vp, ptf, ptm, pts, c0, c1, c2);
+        stage_origin<L>(vp, tf, tm, pts, c0, c1, c2);
         tma_prefetch_3d(&tmap, c0, c1, c2);
       }
     }
-    __syncthreads();  // mbarrier initialised, coordinates published
-    const uint32_t tf = S.tc[0], tm = S.tc[1], ts = S.tc[2];
     const uint32_t tile = tf + vp.ntf * (tm + vp.ntm * ts);  // canonical index (work list, dense list)
     if (vp.use_tma) {
       mbar_wait(&S.mbar, 0);  // every thread waits itself: the TMA writes are visible to it afterwards
@@ -1095,10 +1286,10 @@ k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const P
       __syncthreads();
     }
     int status = TILE_EMPTY;
-    L first, second;
-    if (!region_uniform(S, S.lab + (vp.pad ? 16 / (int)sizeof(L) - 1 : 0), first, second)) {
+    L first;
+    if (!region_uniform(S, S.lab + (vp.pad ? 16 / (int)sizeof(L) - 1 : 0), first)) {
 #if ZM_K2_PATH
-      status = tile_body<L, CO, MODE, true>(vp, o, S, tile, tf, tm, ts, 0, TS, first, second);
+      status = tile_body_k2<L, CO>(vp, o, S, tile, tf, tm, ts, first);
       if (status == TILE_NOT_K2)
 #endif
         status = tile_body<L, CO, MODE>(vp, o, S, tile, tf, tm, ts, 0, TS);

@@ -18,6 +18,8 @@ NotImplementedError; there is no CPU fallback for anything.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 import weakref
 
 import numpy as np
@@ -63,17 +65,18 @@ def as_volume3d(data: np.ndarray, close: bool = False) -> np.ndarray:
 
 
 class _PinnedBlock:
-  """Page-locked host block the bulk device-to-host copy lands in; arrays handed to the user are views
-  of it and keep it alive (the ctypes buffer they are based on references the block)."""
+  """Page-locked host block the bulk device-to-host copy lands in.  Arrays handed to the user are views of the
+  block's ctypes buffer and keep that buffer alive; the memory is returned (cudaFreeHost) by a finalizer on the
+  buffer, i.e. when the mesher has dropped the block AND the last view is gone -- no reference cycle, no __del__."""
 
   def __init__(self, lib, nbytes: int):
-    self._lib = lib
     self.nbytes = max(int(nbytes), 1)
-    self.ptr = lib.zm_host_alloc(self.nbytes)
-    if not self.ptr:
+    ptr = lib.zm_host_alloc(self.nbytes)
+    if not ptr:
       raise MemoryError(f"zmesh_b200: cannot allocate {self.nbytes} bytes of pinned host memory")
-    self._buf = (C.c_ubyte * self.nbytes).from_address(self.ptr)
-    self._buf._zm_owner = self  # arrays -> ctypes buffer -> block
+    self.ptr = ptr
+    self._buf = (C.c_ubyte * self.nbytes).from_address(ptr)
+    weakref.finalize(self._buf, lib.zm_host_free, ptr)
     self._live = []
 
   def view(self, dtype, shape, offset: int) -> np.ndarray:
@@ -84,12 +87,6 @@ class _PinnedBlock:
   def idle(self) -> bool:
     self._live = [r for r in self._live if r() is not None]
     return not self._live
-
-  def __del__(self):
-    try:
-      self._lib.zm_host_free(self.ptr)
-    except Exception:
-      pass
 
 
 class _Stage:
@@ -259,6 +256,16 @@ class Mesher:
       raise ValueError("device arrays must be C- or Fortran-contiguous")
     ptr = int(cai["data"][0])
     self._max_label = (1 << (8 * nbytes)) - 1
+    # order the mesher's stream after the work that produced the array: the stream the interface names (v3), else
+    # torch's current stream for a torch tensor, else the legacy default stream
+    producer = cai.get("stream")
+    if producer is None:
+      torch = sys.modules.get("torch")
+      if torch is not None and isinstance(obj, torch.Tensor):
+        producer = int(torch.cuda.current_stream(obj.device).cuda_stream)
+      else:
+        producer = 1
+    self._check(self._lib.zm_wait_stream(self._h, C.c_void_p(int(producer)) if producer else None))
     self._check(self._call_mesh(ptr, nbytes, s3, c_order, close, 1))
 
   def ids(self):
@@ -301,8 +308,12 @@ class Mesher:
 
   # All labels are finalized on the device by the first get(); their arrays cross PCIe in ONE
   # transfer into pinned host memory and get() hands out per-label views of it (SURVEY.md 8b:
-  # "get() becomes a slice of pinned host memory").  A label asked for twice gets a private copy the
-  # second time, so two results never alias.
+  # "get() becomes a slice of pinned host memory").  Ownership: every label's first result is a view
+  # the caller may mutate freely -- a label asked for AGAIN is read back from the device, so a caller's
+  # in-place edit (mesh.vertices += offset) never shows up in a later get().  The block (12 bytes per
+  # vertex and face of ALL labels; ~20 GB for a 2048^3 volume) stays page-locked while any handed-out
+  # array is alive.  When it cannot be allocated, or is larger than ZMESH_B200_PINNED_LIMIT bytes,
+  # get() falls back to one device-to-host copy per label into ordinary numpy arrays.
   def _pinned(self, nbytes: int) -> _PinnedBlock:
     for b in self._blocks:
       if b.nbytes >= nbytes and b.idle():
@@ -320,9 +331,23 @@ class Mesher:
     self._check(self._lib.zm_finalize(self._h, int(normals), int(voxel_centered), 0,
                                       off.ctypes.data_as(C.POINTER(C.c_float)), C.byref(view)))
     nv, nf, nl = int(view.n_vertices), int(view.n_faces), int(view.n_labels)
-    blk = self._pinned(12 * nv * (2 if normals else 1) + 12 * nf)
     st = _Stage()
     st.key = key
+    st.given = set()
+    nbytes = 12 * nv * (2 if normals else 1) + 12 * nf
+    limit = int(os.environ.get("ZMESH_B200_PINNED_LIMIT", "0") or 0)
+    blk = None
+    if not (limit and nbytes > limit):
+      try:
+        blk = self._pinned(nbytes)
+      except MemoryError:
+        blk = None
+    if blk is None:  # per-label transfers (zm_get) instead of the bulk view
+      st.v = st.f = None
+      st.n = True if normals else None
+      st.index = None
+      self._stage = st
+      return st
     st.v = blk.view(np.float32, (nv, 3), 0)
     st.f = blk.view(np.uint32, (nf, 3), 12 * nv)
     st.n = blk.view(np.float32, (nv, 3), 12 * nv + 12 * nf) if normals else None
@@ -333,7 +358,6 @@ class Mesher:
     voff = np.ctypeslib.as_array(view.voff_host, shape=(nl + 1,)).tolist() if nl else [0]
     foff = np.ctypeslib.as_array(view.foff_host, shape=(nl + 1,)).tolist() if nl else [0]
     st.index = {labels[i]: (voff[i], voff[i + 1], foff[i], foff[i + 1]) for i in range(nl)}
-    st.given = set()
     self._stage = st
     return st
 
@@ -343,17 +367,19 @@ class Mesher:
     key = (voxel_centered, tuple(float(x) for x in self._voxel_res) if voxel_centered else None)
     if st is None or st.key != key or (normals and st.n is None):
       st = self._build_stage(normals or (st is not None and st.key == key and st.n is not None), voxel_centered)
+    if st.index is None:  # no bulk block: one device-to-host copy per label
+      return self._fetch(label, normals, voxel_centered, transpose=False)
     rng = st.index.get(label)
     if rng is None or label in self._erased or rng[3] == rng[2]:
       mesh = Mesh()
       mesh.id = label
       return mesh
-    v, f = st.v[rng[0]:rng[1]], st.f[rng[2]:rng[3]]
-    if label in st.given:
-      v, f = v.copy(), f.copy()
+    if label in st.given:  # the caller already owns (and may have edited) this label's staged arrays
+      return self._fetch(label, normals, voxel_centered, transpose=False)
     st.given.add(label)
     # the reference hands normals back as float64 (zmesh/_zmesh.pyx:151)
-    return Mesh._wrap(v, f, st.n[rng[0]:rng[1]].astype(np.float64) if normals else None, label)
+    return Mesh._wrap(st.v[rng[0]:rng[1]], st.f[rng[2]:rng[3]],
+                      st.n[rng[0]:rng[1]].astype(np.float64) if normals else None, label)
 
   def get_mesh(self, mesh_id, normals=False, simplification_factor=0, max_simplification_error=40,
                voxel_centered=False) -> Mesh:
