@@ -1248,9 +1248,11 @@ __device__ __forceinline__ int tile_body_k2(const VolParams& vp, const Pass1Args
 // MODE 0: one CTA per tile (the hardware CTA scheduler overlaps the TMA wait of one tile with the
 // work of the others resident on the SM).  MODE 1: the queued dense tiles, two half tiles each.
 #ifndef ZM_PREFETCH_LAYERS
-#define ZM_PREFETCH_LAYERS 2
+#define ZM_PREFETCH_LAYERS 1
 #endif
-constexpr uint32_t PREFETCH_LAYERS = ZM_PREFETCH_LAYERS;  // s-layers ahead whose region is pulled into L2 (0: off); c5: 2 layers = 1024 CTAs
+// s-layers ahead whose region is pulled into L2 (0: off).  c5 k_classify ms at 1 / 2 / 3 / 4 layers (512 CTAs each):
+// 27.14 / 27.44 / 28.19 / 28.70; all-zero volume 12.50 / 12.69 / 12.76 / 13.85
+constexpr uint32_t PREFETCH_LAYERS = ZM_PREFETCH_LAYERS;
 template <typename L, bool CO, int MODE>
 __global__ void __launch_bounds__(NT, MODE == 0 ? (sizeof(L) == 8 ? ZM_U64_CTAS : ZM_U32_CTAS) : 1)
 k_classify(const VolParams vp, const __grid_constant__ CUtensorMap tmap, const Pass1Args o) {
