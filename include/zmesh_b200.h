@@ -97,6 +97,15 @@ int zm_directory(zm_handle* h, uint64_t* labels, uint64_t* n_vertices, uint64_t*
  * shards).  Call after zm_mesh_slab and before the first zm_get / zm_finalize / zm_export_plane. */
 int zm_set_label_offsets(zm_handle* h, const uint64_t* labels, const uint32_t* offsets, uint64_t n);
 
+/* The same without a host round trip (all work queued on the handle's stream): zm_export_directory writes this
+ * shard's directory into dst_device[2 * (1 + capacity)] -- word 0 = number of labels, then (label, n_vertices)
+ * pairs; the caller all-gathers the buffers of all shards in rank order (e.g. ncclAllGather on the same stream) and
+ * zm_import_directories(all, world, rank, capacity) sums, per label of this shard, the vertices on earlier shards.
+ * A directory that does not fit `capacity` is reported by the next zm_finalize / zm_get as ZM_ERR_STATE: repeat the
+ * step with a larger capacity. */
+int zm_export_directory(zm_handle* h, uint64_t* dst_device, uint64_t capacity);
+int zm_import_directories(zm_handle* h, const uint64_t* all_device, uint32_t world, uint32_t rank, uint64_t capacity);
+
 /* Writes the cross-shard indices of the in-plane vertex slots of this shard's first plane into
  * dst_device[zm_plane_elems(h)] (uint32 [Em][Efp][4]); the shard below passes the received copy to
  * zm_set_foreign_plane (pointer borrowed until the next zm_mesh*). */
@@ -169,6 +178,12 @@ typedef struct {
 } zm_bulk_view;
 int zm_finalize(zm_handle* h, int normals, int voxel_centered, int transpose,
                 const float centering_offset[3], zm_bulk_view* view);
+
+/* Slab shards that are not the last one: start pass 2 for every tile except the top tile layer -- the only tiles
+ * whose cubes reference the next shard's boundary plane -- without waiting for that plane and without synchronising
+ * (the NCCL transfer of the plane overlaps these tiles).  The zm_finalize that follows, with the same arguments and
+ * after zm_set_foreign_plane, emits the top layer.  A no-op for unsharded volumes and for the last shard. */
+int zm_finalize_begin(zm_handle* h, int normals, int voxel_centered, int transpose, const float centering_offset[3]);
 
 /* Copies the finalized arrays of all labels to host buffers in one transfer each
  * (vertices 3*V_total floats, faces 3*T_total uint32, normals 3*V_total floats or NULL). */

@@ -74,12 +74,15 @@ SYMBOLS = {
   "zm_num_directory": (C.c_uint64, [C.c_void_p]),
   "zm_directory": (C.c_int, [C.c_void_p, _u64p, _u64p, _u64p, C.c_uint64]),
   "zm_set_label_offsets": (C.c_int, [C.c_void_p, _u64p, C.POINTER(C.c_uint32), C.c_uint64]),
+  "zm_export_directory": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+  "zm_import_directories": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64]),
   "zm_plane_elems": (C.c_uint64, [C.c_void_p]),
   "zm_export_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
   "zm_set_foreign_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
   "zm_set_normal_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
   "zm_add_normal_plane": (C.c_int, [C.c_void_p, C.c_void_p]),
   "zm_finish_normals": (C.c_int, [C.c_void_p]),
+  "zm_finalize_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f3]),
   "zm_num_ids": (C.c_uint64, [C.c_void_p]),
   "zm_ids": (C.c_int, [C.c_void_p, _u64p, C.c_uint64]),
   "zm_get_counts": (C.c_int, [C.c_void_p, C.c_uint64, _u64p, _u64p]),

@@ -46,6 +46,8 @@ struct LabelRec {
 };
 
 struct FinalState {
+  bool partial = false;  // slab shard: zm_finalize_begin has emitted all tiles but the top layer (partial_args: its arguments)
+  int partial_args[3] = {0, 0, 0};
   bool faces_valid = false, verts_valid = false, normals_valid = false;
   bool normals_pending = false;  // slab shard: accumulated, awaiting zm_add_normal_plane / zm_finish_normals
   int voxel_centered = 0, transpose = 0, normals_transpose = 0;
@@ -74,6 +76,7 @@ struct zm_handle {
   DevBuf d_faces, d_verts, d_normals;
   DevBuf d_voff, d_tmpA, d_tmpB;     // slab sharding: per-table-slot index offsets; upload scratch
   bool tl_fixed = false, have_voff = false, slab_mode = false;
+  bool dir_exchange = false;  // voff came from zm_import_directories: the exchange's overflow flag is checked by finalize
   const uint32_t* foreign = nullptr;  // borrowed: boundary-plane indices received from the next shard
   float* nplane_out = nullptr;        // borrowed: normal contributions to the next shard's first-plane vertices
   uint64_t capL = 0;
@@ -269,6 +272,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
     return fail(h, ZM_ERR_UNSUPPORTED, "extent exceeds the 21-bit half-voxel key range (2^20 voxels per axis)");
   h->tl_fixed = false;
   h->have_voff = false;
+  h->dir_exchange = false;
   h->foreign = nullptr;
   h->nplane_out = nullptr;
   h->slab_mode = slab != nullptr;
@@ -490,7 +494,10 @@ Pass2Args pass2_args(zm_handle* h) {
 
 // Pass 2 (lazy): faces once per zm_mesh; vertices per (voxel_centered, transpose, offset); normals per
 // transpose.  Everything is written in its final layout on the device.
-int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, const float* off) {
+// begin_only (slab shards that are not the last): launch pass 2 for every tile but the top layer -- the only ones
+// whose cubes reference the next shard's boundary plane -- and return without synchronising; the finalize that
+// follows (same arguments, after zm_set_foreign_plane) emits the top layer.
+int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, const float* off, bool begin_only = false) {
   if (h->failed) return fail(h, ZM_ERR_STATE, "the last zm_mesh failed; mesh again before reading results");
   float o[3] = {h->res[0], h->res[1], h->res[2]};
   if (off) { o[0] = off[0]; o[1] = off[1]; o[2] = off[2]; }
@@ -501,13 +508,19 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
   const bool need_normals = normals && !(f.normals_valid && f.normals_transpose == transpose);
   const bool need_faces = !f.faces_valid;
   if (same_verts && !need_normals && !need_faces) return ZM_OK;
+  const bool has_foreign = h->vp.Es_own < h->vp.Es;  // (a slab shard that is not the last)
+  if (begin_only && (!has_foreign || !h->Vtot || !h->n_work || f.partial)) return ZM_OK;  // nothing to split
+  if (f.partial && (f.partial_args[0] != normals || f.partial_args[1] != voxel_centered || f.partial_args[2] != transpose))
+    return fail(h, ZM_ERR_STATE, "slab shard: zm_finalize must repeat the arguments of zm_finalize_begin");
   ZM_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t st = h->stream;
   uint32_t launches = 0;
-  ZM_CUDA(h, cudaEventRecord(h->ev[5], st));
-  ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
+  if (!f.partial) {
+    ZM_CUDA(h, cudaEventRecord(h->ev[5], st));
+    ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
+  }
   if (h->Vtot && h->n_work) {
-    if (h->vp.Es_own < h->vp.Es && !h->foreign)
+    if (has_foreign && !h->foreign && !begin_only)
       return fail(h, ZM_ERR_STATE, "slab shard: zm_set_foreign_plane must be called before the first get/finalize");
     if (normals && h->slab_mode && f.normals_pending)
       return fail(h, ZM_ERR_STATE, "slab shard: normals await zm_add_normal_plane / zm_finish_normals");
@@ -517,7 +530,7 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     if (rc != ZM_OK) return rc;
     ZM_CUDA(h, h->d_faces.ensure((size_t)h->Ttot * 12));
     ZM_CUDA(h, h->d_verts.ensure((size_t)h->Vtot * 12));
-    if (need_normals) {
+    if (need_normals && !f.partial) {
       ZM_CUDA(h, h->d_normals.ensure((size_t)h->Vtot * 12));
       ZM_CUDA(h, cudaMemsetAsync(h->d_normals.p, 0, (size_t)h->Vtot * 12, st));
       if (h->slab_mode && h->nplane_out)
@@ -533,6 +546,8 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     a.transpose = transpose;
     a.write_faces = need_faces ? 1 : 0;
     a.write_verts = same_verts ? 0 : 1;
+    a.layer_mode = begin_only ? 1u : (f.partial ? 2u : 0u);
+    a.top_tile_lo = h->vp.ntf * h->vp.ntm * (h->vp.nts - 1u);
     {
       CUtensorMap rmap;
       if (!make_rowinfo_map(&rmap, h->d_rowinfo.p, h->vp)) return fail(h, ZM_ERR_CUDA, "cuTensorMapEncodeTiled(rowinfo) failed");
@@ -544,6 +559,12 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
       ZM_CUDA(h, cudaGetLastError());
       ++launches;
     }
+    if (begin_only) {
+      f.partial = true;
+      f.partial_args[0] = normals; f.partial_args[1] = voxel_centered; f.partial_args[2] = transpose;
+      h->stats.launches_finalize = launches;
+      return ZM_OK;
+    }
     ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
     if (need_normals && !h->slab_mode) {  // (slab shards normalise in zm_finish_normals, after the plane exchange)
       k_normals_normalize<<<grid_for(h->Vtot, 256), 256, 0, st>>>(h->d_normals.as<float>(), h->Vtot);
@@ -552,11 +573,16 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     }
   }
   ZM_CUDA(h, cudaEventRecord(h->ev[7], st));
+  if (h->dir_exchange)  // (device-side directory exchange: its overflow flag travels with this synchronisation)
+    ZM_CUDA(h, cudaMemcpyAsync(&h->h_ctl->flags, &h->d_ctl.as<Control>()->flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   ZM_CUDA(h, cudaStreamSynchronize(st));
+  if (h->dir_exchange && (h->h_ctl->flags & FLAG_DIR))
+    return fail(h, ZM_ERR_STATE, "slab shard: a label directory did not fit the exchange buffer; repeat the step with a larger capacity");
   cudaEventElapsedTime(&h->stats.ms_faces, h->ev[5], h->ev[6]);
   cudaEventElapsedTime(&h->stats.ms_vertices, h->ev[6], h->ev[7]);
   cudaEventElapsedTime(&h->stats.ms_finalize, h->ev[5], h->ev[7]);
-  h->stats.launches_finalize = launches;
+  h->stats.launches_finalize = launches + (f.partial ? h->stats.launches_finalize : 0u);
+  f.partial = false;
   f.faces_valid = true;
   f.verts_valid = true;
   f.voxel_centered = voxel_centered;
@@ -740,6 +766,42 @@ int zm_set_label_offsets(zm_handle* h, const uint64_t* labels, const uint32_t* o
   return ZM_OK;
 }
 
+int zm_export_directory(zm_handle* h, uint64_t* dst_device, uint64_t capacity) {
+  if (!h || !dst_device) return ZM_ERR_INVALID;
+  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  if (!h->n_work && h->recs.empty()) {  // nothing meshed on this shard (degenerate slab): an empty directory
+    ZM_CUDA(h, cudaMemsetAsync(dst_device, 0, 16, h->stream));
+    return ZM_OK;
+  }
+  k_export_directory<<<grid_for(h->recs.size() + 1, 256), 256, 0, h->stream>>>(h->d_list.as<u64>(), h->d_ctl.as<Control>(),
+                                                                               (u64*)dst_device, capacity);
+  ZM_CUDA(h, cudaGetLastError());
+  return ZM_OK;
+}
+
+int zm_import_directories(zm_handle* h, const uint64_t* all_device, uint32_t world, uint32_t rank, uint64_t capacity) {
+  if (!h || !all_device || rank >= world) return ZM_ERR_INVALID;
+  if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
+  if (h->tl_fixed) return fail(h, ZM_ERR_STATE, "label offsets must be set before the first get/finalize/export");
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  // a shard without output still takes part in the overflow check, so that all shards take the same decision
+  ZM_CUDA(h, h->d_ctl.ensure(sizeof(Control)));
+  const bool have_table = h->n_work != 0 && h->d_keys.p && h->d_cnt.p;
+  const uint32_t cap = have_table ? h->hash_cap : 1u;
+  ZM_CUDA(h, h->d_voff.ensure((size_t)cap * 4));
+  ZM_CUDA(h, cudaMemsetAsync(h->d_voff.p, 0, (size_t)cap * 4, h->stream));
+  if (!have_table) ZM_CUDA(h, cudaMemsetAsync(h->d_ctl.p, 0, sizeof(Control), h->stream));
+  LabelTable ht{h->d_keys.as<u64>(), h->d_cnt.as<u64>(), cap - 1};
+  const dim3 grid(std::min<uint32_t>(grid_for(std::min<uint64_t>(capacity, 1u << 20), 256), 64u), world);
+  k_import_directories<<<grid, 256, 0, h->stream>>>(ht, (const u64*)all_device, have_table ? rank : 0u, capacity,
+                                                    h->d_voff.as<uint32_t>(), h->d_ctl.as<Control>());
+  ZM_CUDA(h, cudaGetLastError());
+  h->have_voff = have_table;
+  h->dir_exchange = true;
+  return ZM_OK;
+}
+
 uint64_t zm_plane_elems(zm_handle* h) { return h ? 4ull * h->vp.Em * h->vp.Efp : 0; }
 
 int zm_export_plane(zm_handle* h, uint32_t* dst_device) {
@@ -894,6 +956,11 @@ int zm_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     view->normals_dev = (normals && h->fin.normals_valid && h->Vtot) ? h->d_normals.as<float>() : nullptr;
   }
   return ZM_OK;
+}
+
+int zm_finalize_begin(zm_handle* h, int normals, int voxel_centered, int transpose, const float centering_offset[3]) {
+  if (!h) return ZM_ERR_INVALID;
+  return do_finalize(h, normals, voxel_centered, transpose, centering_offset, true);
 }
 
 int zm_fetch_all(zm_handle* h, float* vertices, uint32_t* faces, float* normals_out) {

@@ -86,7 +86,8 @@ template <typename L> struct RowPad { static constexpr int value = ((TF + 1) * (
 enum : uint32_t {
   FLAG_HASH_FULL = 1u,  // global label table too small -> host grows it and reruns pass 1
   FLAG_CAP = 2u,        // perm / record / tile-label capacity guess too small -> host reruns pass 1
-  FLAG_INTERNAL = 4u    // invariant violated
+  FLAG_INTERNAL = 4u,   // invariant violated
+  FLAG_DIR = 8u         // slab sharding: a shard's label directory did not fit the exchange buffer
 };
 
 // capacities of the per-tile shared-memory structures.  MODE 0 covers ordinary segmentations;
@@ -1472,6 +1473,46 @@ __global__ void __launch_bounds__(256) k_set_voff(const LabelTable ht, const u64
   }
 }
 
+// slab sharding, device-side directory exchange: every shard publishes its (label, vertices) list in a fixed-capacity
+// buffer -- word 0 = number of labels, then (label, n_vertices) pairs -- which is all-gathered over NCCL on the
+// mesher's stream; each shard then sums, per label, the vertices on EARLIER shards into voff[] (indexed by its own
+// label-table slot).  No host round trip (the host-side path of zmesh_b200/sharded.py cost 0.8 ms per step at 8 GPUs).
+__global__ void __launch_bounds__(256) k_export_directory(const u64* list, const Control* ctl, u64* dst, u64 capacity) {
+  const u64 n = ctl->totals[0];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { dst[0] = n; dst[1] = 0ull; }
+  const u64 m = n < capacity ? n : capacity;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (u64)gridDim.x * blockDim.x) {
+    dst[2 + 2 * i] = list[3 * i];
+    dst[3 + 2 * i] = list[3 * i + 1];
+  }
+}
+
+// all: [world][1 + capacity][2] u64.  grid.y = shard q (every shard checks EVERY directory for overflow, so that all
+// shards take the same decision; only the earlier ones, q < rank, contribute offsets).
+__global__ void __launch_bounds__(256) k_import_directories(const LabelTable ht, const u64* all, uint32_t rank, u64 capacity,
+                                                            uint32_t* voff, Control* ctl) {
+  const uint32_t q = blockIdx.y;
+  const u64* src = all + (size_t)q * 2 * (1 + capacity);
+  const u64 n = src[0];
+  if (n > capacity) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&ctl->flags, FLAG_DIR);
+    return;
+  }
+  if (q >= rank) return;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) {
+    const u64 label = src[2 + 2 * i];
+    const uint32_t nv = (uint32_t)src[3 + 2 * i];
+    if (label == 0ull || nv == 0u) continue;
+    uint32_t h = hash_label(label) & ht.mask;
+    for (uint32_t p = 0; p <= ht.mask && p < 4096u; ++p) {
+      const u64 k = ht.keys[h];
+      if (k == label) { atomicAdd(&voff[h], nv); break; }
+      if (k == 0ull) break;  // (the label does not occur on this shard)
+      h = (h + 1u) & ht.mask;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // pass 2
 
@@ -1489,6 +1530,9 @@ struct Pass2Args {
   uint32_t n_work;
   int voxel_centered, transpose;
   int write_faces, write_verts;
+  // slab sharding: 0 = all tiles; 1 = all but the top tile layer (tiles >= top_tile_lo: the only ones whose cubes
+  // reference the boundary plane of the next shard), launched while that plane is still in flight; 2 = only the top layer
+  uint32_t layer_mode, top_tile_lo;
   const uint32_t* foreign;  // slab sharding: final indices of the top plane's slots, [Em][Efp][4], from the next shard
   float* fnormals;          // slab sharding + normals: contributions to the next shard's first-plane vertices, [Em][Efp][4][3]
 };
@@ -1605,6 +1649,7 @@ constexpr int EMIT_NC = ZM_EMIT_CONSUMERS;           // consumer warps
 constexpr int EMIT_ST = ZM_EMIT_STAGES;              // tiles in flight per CTA
 constexpr int EMIT_THREADS = 32 * (EMIT_NC + 1);     // + the producer warp
 constexpr int TLC = 64;                      // tile-local labels whose tl entry is cached in shared memory
+constexpr uint32_t EMIT_END = 0xFFFFFFFFu;   // header.tile of the end marker the producer publishes after its last tile
 
 __device__ __forceinline__ void mbar_arrive(u64* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -1651,9 +1696,17 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
     TileHdr hn;
     hn.tile = 0; hn.nlab = 0; hn.tlbase = 0;
     if (lane == 0) hn = load_hdr(a.hdr + first);
+    uint32_t pub = 0;  // tiles published so far (the consumers see exactly these, then the end marker)
     for (uint32_t it = 0; it < ntile; ++it) {
-      const int s = it % EMIT_ST;
-      const uint32_t k = it / EMIT_ST;  // k-th use of stage s
+      const uint32_t tilev = __shfl_sync(FULL, hn.tile, 0);
+      const bool pass = !SLAB || a.layer_mode == 0u || ((tilev >= a.top_tile_lo) == (a.layer_mode == 2u));
+      if (!pass) {
+        if (lane == 0 && it + 1 < ntile) hn = load_hdr(a.hdr + first + (size_t)(it + 1) * G);
+        continue;
+      }
+      const int s = pub % EMIT_ST;
+      const uint32_t k = pub / EMIT_ST;  // k-th use of stage s
+      ++pub;
       if (k > 0) mbar_wait(&empty[s], (k - 1) & 1u);  // every consumer warp has released the stage
       if (lane == 0) {
         s_hdr[s] = hn;
@@ -1681,16 +1734,24 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready[s]);  // (release: header, tl cache and slot bases are visible to the waiters)
     }
+    {  // end marker: a header without a tile
+      const int s = pub % EMIT_ST;
+      const uint32_t k = pub / EMIT_ST;
+      if (k > 0) mbar_wait(&empty[s], (k - 1) & 1u);
+      if (lane == 0) {
+        s_hdr[s].tile = EMIT_END;
+        mbar_arrive(&ready[s]);
+      }
+    }
     return;
   }
 
   // ================= consumer warps =================
   const int cw = warp;
-  for (uint32_t it = 0; it < ntile; ++it) {
+  for (uint32_t it = 0;; ++it) {
     const int s = it % EMIT_ST;
     const uint32_t k = it / EMIT_ST;
     mbar_wait(&ready[s], k & 1u);
-    mbar_wait(&full[s], k & 1u);  // (already complete: makes the TMA-written region visible to this thread)
     TileHdr h;
     {
       union { uint4 q[2]; TileHdr h; } u;
@@ -1698,6 +1759,8 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
       u.q[1] = reinterpret_cast<const uint4*>(&s_hdr[s])[1];
       h = u.h;
     }
+    if (h.tile == EMIT_END) break;  // the producer has published all of the CTA's tiles
+    mbar_wait(&full[s], k & 1u);  // (already complete: makes the TMA-written region visible to this thread)
     uint32_t b = h.tile;
     const uint32_t tf = b % vp.ntf;
     b /= vp.ntf;

@@ -205,6 +205,13 @@ class Mesher:
     self._check(self._lib.zm_set_label_offsets(self._h, labels.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                offsets.ctypes.data_as(C.POINTER(C.c_uint32)), labels.size))
 
+  def export_directory(self, dst_device_ptr: int, capacity: int):
+    """Device-side directory exchange (no host round trip): see zm_export_directory."""
+    self._check(self._lib.zm_export_directory(self._h, C.c_void_p(int(dst_device_ptr)), int(capacity)))
+
+  def import_directories(self, all_device_ptr: int, world: int, rank: int, capacity: int):
+    self._check(self._lib.zm_import_directories(self._h, C.c_void_p(int(all_device_ptr)), int(world), int(rank), int(capacity)))
+
   def plane_elems(self) -> int:
     return int(self._lib.zm_plane_elems(self._h))
 
@@ -431,6 +438,12 @@ class Mesher:
       "n_vertices": int(view.n_vertices), "n_faces": int(view.n_faces),
       "vertices_dev": view.vertices_dev, "faces_dev": view.faces_dev, "normals_dev": view.normals_dev,
     }
+
+  def finalize_begin(self, normals=False, voxel_centered=False, transpose=False):
+    """Slab shards: start pass 2 for all tiles but the top layer (see zm_finalize_begin); follow with finalize()."""
+    off = _f3(self._voxel_res)
+    self._check(self._lib.zm_finalize_begin(self._h, int(bool(normals)), int(bool(voxel_centered)), int(bool(transpose)),
+                                            off.ctypes.data_as(C.POINTER(C.c_float))))
 
   def fetch_all(self, normals=False):
     """After finalize(): all labels' arrays in one device-to-host transfer each."""

@@ -9,7 +9,9 @@ to rank r+1, so every vertex exists exactly once across ranks as well -- per-lab
 CONCATENATE, there is nothing to dedup.  What has to be exchanged is only bookkeeping:
 
   1. all-gather of every rank's (label, n_vertices) directory -> rank r's face indices of label L
-     are shifted by the number of L's vertices on ranks < r (`label_offsets`);
+     are shifted by the number of L's vertices on ranks < r (`label_offsets`).  With a CUDA input and
+     NCCL this runs entirely on the device (zm_export_directory -> all_gather_into_tensor on the
+     mesher's stream -> zm_import_directories); the host-side functions below are the gloo / test path;
   2. rank r+1 sends rank r the final indices of the vertex slots in the shared plane
      (uint32 [Em][Efp][4], one NCCL send/recv between neighbours), which rank r's face kernel
      reads for the corners of its top cube layer.
@@ -128,7 +130,8 @@ class ShardedMesher:
     self._plane_recv = None
     self._nplane_out = None
     self._nplane_in = None
-    self._dir = None
+    self._dir_cap = 1 << 15  # labels per shard the device-side directory exchange holds (doubles on overflow)
+    self._dir_bufs = None
 
   def planes(self, full_extent: int, close: bool = False):
     return slab_planes(int(full_extent), bool(close), self.rank, self.world)
@@ -144,20 +147,37 @@ class ShardedMesher:
     tm = self._timer()
     m.mesh_slab(data, full_extent, buf_lo, cube_lo, cube_hi, last, close=close)
     tm("pass1")
-    labels, nv, nt = m.directory()
     dev = f"cuda:{self.device}"
-    ls, ns = all_gather_directories(labels, nv, self.group, dev)
-    tm("all_gather")
-    m.set_label_offsets(labels, offsets_from_directories(ls, ns, self.rank))
-    tm("offsets")
-    self._dir = (labels, nv, nt)
-    # boundary plane: rank r+1 -> rank r.  When the mesher queues its kernels on torch's current stream
-    # (Mesher.set_stream, as bench.py does) the export kernel, the NCCL transfer and pass 2 are ordered
-    # on the device and no host synchronisation is needed.
-    n = m.plane_elems()
-    ops = []
     stream = torch.cuda.current_stream()
     same_stream = m.stream_handle() == int(stream.cuda_stream)
+    on_device = hasattr(data, "__cuda_array_interface__") and dist.get_backend(self.group) == "nccl"
+    if on_device:
+      # device-side directory exchange: nothing crosses PCIe, nothing blocks the host
+      cap = self._dir_cap
+      if self._dir_bufs is None or self._dir_bufs[0].numel() != 2 * (1 + cap):
+        self._dir_bufs = (torch.empty(2 * (1 + cap), dtype=torch.int64, device=dev),
+                          torch.empty(self.world * 2 * (1 + cap), dtype=torch.int64, device=dev))
+      mine, allb = self._dir_bufs
+      m.export_directory(mine.data_ptr(), cap)
+      if not same_stream:
+        m.sync()
+      dist.all_gather_into_tensor(allb, mine, group=self.group)
+      if not same_stream:
+        stream.synchronize()
+      m.import_directories(allb.data_ptr(), self.world, self.rank, cap)
+      tm("all_gather")
+    else:
+      labels, nv, nt = m.directory()
+      ls, ns = all_gather_directories(labels, nv, self.group, dev)
+      tm("all_gather")
+      m.set_label_offsets(labels, offsets_from_directories(ls, ns, self.rank))
+      tm("offsets")
+    # boundary plane: rank r+1 -> rank r.  When the mesher queues its kernels on torch's current stream
+    # (Mesher.set_stream, as bench.py does) the export kernel, the NCCL transfer and pass 2 are ordered
+    # on the device and no host synchronisation is needed; pass 2 of every tile below the top tile layer
+    # (finalize_begin) is queued BEFORE the stream waits for the transfer, so the transfer overlaps it.
+    n = m.plane_elems()
+    ops = []
     if self.rank > 0:
       if self._plane_send is None or self._plane_send.numel() != n:
         self._plane_send = torch.empty(n, dtype=torch.int32, device=dev)
@@ -169,20 +189,32 @@ class ShardedMesher:
       if self._plane_recv is None or self._plane_recv.numel() != n:
         self._plane_recv = torch.empty(n, dtype=torch.int32, device=dev)
       ops.append(dist.P2POp(dist.irecv, self._plane_recv, self.rank + 1, group=self.group))
-    if ops:
-      for w in dist.batch_isend_irecv(ops):
-        w.wait()  # makes the current stream wait for the transfer (no host block)
-      if not same_stream:
-        stream.synchronize()
-    m.set_foreign_plane(self._plane_recv.data_ptr() if not last else None)
-    tm("plane_exchange")
-    out = None
-    if finalize or normals:
-      if normals and not last:
+    works = dist.batch_isend_irecv(ops) if ops else []
+    want_pass2 = finalize or normals
+    if want_pass2 and not last:
+      if normals:
         if self._nplane_out is None or self._nplane_out.numel() != 3 * n:
           self._nplane_out = torch.empty(3 * n, dtype=torch.float32, device=dev)
         m.set_normal_plane(self._nplane_out.data_ptr())
-      out = m.finalize(normals=normals, voxel_centered=voxel_centered)
+      if same_stream:
+        m.finalize_begin(normals=normals, voxel_centered=voxel_centered)
+    for w in works:
+      w.wait()  # makes the current stream wait for the transfer (no host block)
+    if works and not same_stream:
+      stream.synchronize()
+    m.set_foreign_plane(self._plane_recv.data_ptr() if not last else None)
+    tm("plane_exchange")
+    out = None
+    if want_pass2:
+      try:
+        out = m.finalize(normals=normals, voxel_centered=voxel_centered)
+      except RuntimeError as e:
+        if "exchange buffer" not in str(e):
+          raise
+        # (every rank checks every directory size, so every rank takes this branch) repeat the step with a larger buffer
+        self._dir_cap *= 4
+        return self.mesh_slab(data, full_extent, buf_lo, close=close, finalize=finalize, voxel_centered=voxel_centered,
+                              normals=normals)
       tm("pass2")
       if normals:
         # normal contributions of the top cube layer to the next shard's first-plane vertices: rank r -> r+1
