@@ -430,14 +430,17 @@ def main():
   barrier()
   if sm is not None and getattr(sm, "timings", None):
     sm.timings.clear()  # (ZM_SHARD_TIMING diagnostics: steady state only)
-  acc = {k: 0.0 for k in ("ms_classify", "ms_scan", "ms_faces", "ms_vertices", "ms_total", "ms_finalize")}
+  acc = {k: 0.0 for k in ("ms_classify", "ms_scan", "ms_faces", "ms_vertices", "ms_total", "ms_finalize", "ms_exchange")}
   launches = 0
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   with ClockSampler(dev) as clocks:
     barrier()
     ev0.record(stream)
+    host_ms = 0.0
     for _ in range(args.steps):
+      t_h = time.perf_counter()
       st = step()
+      host_ms += (time.perf_counter() - t_h) * 1e3
       for k in acc:
         acc[k] += st[k]
       launches += st["launches"] + st["launches_finalize"]
@@ -450,6 +453,13 @@ def main():
     ms = float(t.item())
     cnt = torch.tensor([st["n_vertices"], st["n_faces"], st["n_labels"]], device=f"cuda:{dev}", dtype=torch.int64)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    # per-rank kernel times (the step is paced by the slowest rank of every phase: the exchanges couple the ranks)
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, {"k_classify": acc["ms_classify"] / args.steps,
+                                      "k_emit": (acc["ms_faces"] + acc["ms_vertices"]) / args.steps,
+                                      "exchange": acc["ms_exchange"] / args.steps, "mesh_call": acc["ms_total"] / args.steps,
+                                      "host_step_ms": host_ms / args.steps,
+                                      "non_empty_tiles": int(st["n_active_tiles"])})
     totV, totT, nlabels_total = int(cnt[0]), int(cnt[1]), int(cnt[2])  # (labels: summed over ranks, a label spanning k slabs counts k times)
   else:
     totV, totT, nlabels_total = st["n_vertices"], st["n_faces"], st["n_labels"]
@@ -591,6 +601,7 @@ def main():
       "details": {"labels": int(nlabels_total), "vertices": int(totV), "faces": int(totT), "volume_gb_per_rank": nvox_local * label_bytes / 1e9,
                   "tiles": {"all": int(st["n_tiles"]), "non_empty": int(st["n_active_tiles"]), "dense_redo": int(st["n_dense_tiles"])}},
       "parity_on_sample": (cpu or {}).get("parity_on_sample"), "nccl_parity": nccl_parity,
+      "per_rank": per_rank if world > 1 else None,
       "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
       "clocks": clocks.summary(),
     }

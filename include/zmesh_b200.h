@@ -205,7 +205,7 @@ typedef struct {
   float ms_h2d, ms_classify, ms_scan, ms_total; /* CUDA-event times of the last zm_mesh          */
   float ms_faces, ms_vertices, ms_finalize;     /* last zm_finalize / first zm_get (pass 2): the fused emit
                                                    kernel, the normals normalisation (0 without normals), both */
-  float reserved;
+  float ms_exchange;  /* zm_slab_step: directory all-gather + boundary-plane transfer, incl. the wait for the slowest shard */
 } zm_stats_t;
 int zm_stats(zm_handle* h, zm_stats_t* out);
 
@@ -217,6 +217,28 @@ int zm_stats(zm_handle* h, zm_stats_t* out);
 int zm_synth_voronoi(void* dst_device, int label_bytes, const uint64_t shape[3], const uint64_t origin[3],
                      const uint64_t full_shape[3], uint32_t pitch, uint64_t seed, int c_order,
                      void* cuda_stream);
+
+/* ---- native multi-GPU step (one process per GPU; no reference counterpart) -------------------------------------
+ * The whole slab step of zmesh_b200/sharded.py in ONE call, with NCCL driven from C++ (bound at run time with
+ * dlopen("libnccl.so.2"); inside a torch process that is the library torch loaded): zm_mesh_slab -> directory
+ * all-gather (ncclAllGather on the handle's stream) -> boundary-plane send/recv on a side stream overlapped with pass 2
+ * of every tile below the top layer -> pass 2 of the top layer (-> the normals plane exchange).  The host issues a
+ * dozen launches after the one synchronisation zm_mesh_slab needs; the Python/torch.distributed path costs ~2 ms of
+ * exposed host time per step at 8 GPUs.
+ *   zm_nccl_unique_id   128-byte ncclUniqueId (call on one rank, broadcast the bytes by any means; two are needed)
+ *   zm_comm_init        ncclCommInitRank for this handle's device: one communicator for the collectives, one for the
+ *                       neighbour transfers
+ *   zm_slab_range       the cube planes [cube_lo, cube_hi) of `rank` and the input planes [in_lo, in_hi) it must supply
+ *   zm_slab_step        `labels` holds input planes [buf_lo, buf_lo + extent along the slab axis) covering that range;
+ *                       finalize / normals / voxel_centered as zm_finalize (results stay distributed: zm_get returns
+ *                       this shard's part of a label, face indices are cross-shard) */
+int zm_nccl_unique_id(void* out128);
+int zm_comm_init(zm_handle* h, const void* id_collectives, const void* id_neighbours, int world, int rank);
+int zm_comm_destroy(zm_handle* h);
+int zm_slab_range(uint64_t full_extent, int close, int rank, int world, zm_slab* slab, uint64_t* in_lo, uint64_t* in_hi);
+int zm_slab_step(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz, int c_order,
+                 int close, int mem_kind, uint64_t full_extent, uint64_t buf_lo, int finalize, int normals,
+                 int voxel_centered, const float centering_offset[3]);
 
 /* Blocks until all work queued by this handle has finished. */
 int zm_sync(zm_handle* h);

@@ -41,7 +41,7 @@ class zm_stats_t(C.Structure):
     ("hash_capacity", C.c_uint64), ("perm_capacity", C.c_uint64),
     ("attempts", C.c_uint32), ("launches", C.c_uint32), ("used_tma", C.c_uint32), ("launches_finalize", C.c_uint32),
     ("ms_h2d", C.c_float), ("ms_classify", C.c_float), ("ms_scan", C.c_float), ("ms_total", C.c_float),
-    ("ms_faces", C.c_float), ("ms_vertices", C.c_float), ("ms_finalize", C.c_float), ("reserved", C.c_float),
+    ("ms_faces", C.c_float), ("ms_vertices", C.c_float), ("ms_finalize", C.c_float), ("ms_exchange", C.c_float),
   ]
 
 
@@ -95,6 +95,12 @@ SYMBOLS = {
   "zm_host_alloc": (C.c_void_p, [C.c_uint64]),
   "zm_host_free": (None, [C.c_void_p]),
   "zm_stats": (C.c_int, [C.c_void_p, C.POINTER(zm_stats_t)]),
+  "zm_nccl_unique_id": (C.c_int, [C.c_void_p]),
+  "zm_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+  "zm_comm_destroy": (C.c_int, [C.c_void_p]),
+  "zm_slab_range": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(zm_slab), _u64p, _u64p]),
+  "zm_slab_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                             C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, _f3]),
   "zm_sync": (C.c_int, [C.c_void_p]),
   "zm_last_error": (C.c_char_p, [C.c_void_p]),
   "zm_version": (C.c_char_p, []),

@@ -4,6 +4,8 @@
 // per-label results on the device, orchestrates classify -> scan -> emit -> final gather on one
 // CUDA stream, and hands label ranges back to the caller.  No CPU compute path exists here.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound at run time (nccl_api), the single-GPU path never needs it
 
 #include <algorithm>
 #include <cstdio>
@@ -77,6 +79,14 @@ struct zm_handle {
   DevBuf d_voff, d_tmpA, d_tmpB;     // slab sharding: per-table-slot index offsets; upload scratch
   bool tl_fixed = false, have_voff = false, slab_mode = false;
   bool dir_exchange = false;  // voff came from zm_import_directories: the exchange's overflow flag is checked by finalize
+  // native multi-GPU step (zm_comm_init / zm_slab_step): one communicator for the collectives on `stream`, one for the
+  // neighbour transfers on `comm_stream` (so that they overlap pass 2), buffers owned by the handle
+  ncclComm_t comm = nullptr, comm_p2p = nullptr;
+  int world = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_comm[2] = {nullptr, nullptr};
+  uint64_t dir_cap = 1ull << 15;
+  DevBuf d_dir_mine, d_dir_all, d_plane_send, d_plane_recv, d_nplane_out, d_nplane_in;
   const uint32_t* foreign = nullptr;  // borrowed: boundary-plane indices received from the next shard
   float* nplane_out = nullptr;        // borrowed: normal contributions to the next shard's first-plane vertices
   uint64_t capL = 0;
@@ -150,11 +160,13 @@ KernelSet kernel_set(int label_bytes, bool c_order) {
   }
 }
 
-pass2_fn emit_kernel(bool c_order, bool normals, bool slab) {
-  if (slab && normals) return c_order ? k_emit<true, true, true> : k_emit<false, true, true>;
-  if (slab) return c_order ? k_emit<true, false, true> : k_emit<false, false, true>;
-  if (c_order) return normals ? k_emit<true, true, false> : k_emit<true, false, false>;
-  return normals ? k_emit<false, true, false> : k_emit<false, false, false>;
+template <bool CO, bool NORMALS>
+pass2_fn emit_kernel_slab(int slab) {
+  return slab == 0 ? k_emit<CO, NORMALS, 0> : (slab == 1 ? k_emit<CO, NORMALS, 1> : k_emit<CO, NORMALS, 2>);
+}
+pass2_fn emit_kernel(bool c_order, bool normals, int slab) {
+  if (c_order) return normals ? emit_kernel_slab<true, true>(slab) : emit_kernel_slab<true, false>(slab);
+  return normals ? emit_kernel_slab<false, true>(slab) : emit_kernel_slab<false, false>(slab);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
@@ -551,7 +563,9 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     {
       CUtensorMap rmap;
       if (!make_rowinfo_map(&rmap, h->d_rowinfo.p, h->vp)) return fail(h, ZM_ERR_CUDA, "cuTensorMapEncodeTiled(rowinfo) failed");
-      pass2_fn fn = emit_kernel(h->c_order, need_normals, h->slab_mode);
+      // slab shards: the launch that excludes the top tile layer never looks at the boundary plane
+      const int slab_kind = !h->slab_mode ? 0 : ((begin_only || !has_foreign) ? 1 : 2);
+      pass2_fn fn = emit_kernel(h->c_order, need_normals, slab_kind);
       int per_sm = 0;
       ZM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, EMIT_THREADS, 0));
       const uint32_t grid = std::min<uint32_t>(h->n_work, (uint32_t)(h->num_sms * std::max(per_sm, 1)));
@@ -599,6 +613,55 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
   }
   return ZM_OK;
 }
+
+// ---- NCCL, bound at run time (dlopen): inside a torch process this resolves to the library torch already loaded ----
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+
+const NcclApi& nccl_api() {
+  static NcclApi api = []() {
+    NcclApi a;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+    if (!lib) return a;
+    auto sym = [&](const char* n) { return dlsym(lib, n); };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+    a.Send = (decltype(a.Send))sym("ncclSend");
+    a.Recv = (decltype(a.Recv))sym("ncclRecv");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.Send && a.Recv && a.GroupStart &&
+           a.GroupEnd && a.GetErrorString;
+    return a;
+  }();
+  return api;
+}
+
+#define ZM_NCCL(h, call)                                                                                   \
+  do {                                                                                                     \
+    ncclResult_t _r = (call);                                                                              \
+    if (_r != ncclSuccess) {                                                                               \
+      char _b[512];                                                                                        \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(_r), __FILE__, __LINE__); \
+      (h)->err = _b;                                                                                       \
+      return ZM_ERR_CUDA;                                                                                  \
+    }                                                                                                      \
+  } while (0)
 
 }  // namespace
 
@@ -651,6 +714,7 @@ int zm_create(const float resolution[3], int device, zm_handle** out) {
 
 void zm_destroy(zm_handle* h) {
   if (!h) return;
+  zm_comm_destroy(h);
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_vol, &h->d_keys, &h->d_cnt, &h->d_offV, &h->d_offT, &h->d_list, &h->d_partial, &h->d_ctl,
@@ -1033,6 +1097,155 @@ int zm_stats(zm_handle* h, zm_stats_t* out) {
   if (!h || !out) return ZM_ERR_INVALID;
   *out = h->stats;
   return ZM_OK;
+}
+
+int zm_nccl_unique_id(void* out128) {
+  if (!out128) return ZM_ERR_INVALID;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  const NcclApi& N = nccl_api();
+  if (!N.ok) { g_create_error = "libnccl.so.2 could not be loaded"; return ZM_ERR_UNSUPPORTED; }
+  ncclUniqueId id;
+  if (N.GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return ZM_ERR_CUDA; }
+  memcpy(out128, &id, 128);
+  return ZM_OK;
+}
+
+int zm_comm_destroy(zm_handle* h) {
+  if (!h) return ZM_ERR_INVALID;
+  if (!h->comm && !h->comm_p2p && !h->comm_stream) return ZM_OK;  // (never touch NCCL -- not even load it -- without a communicator)
+  const NcclApi& N = nccl_api();
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  if (h->comm && N.ok) N.CommDestroy(h->comm);
+  if (h->comm_p2p && N.ok) N.CommDestroy(h->comm_p2p);
+  h->comm = h->comm_p2p = nullptr;
+  for (auto& ev : h->ev_comm) { if (ev) cudaEventDestroy(ev); ev = nullptr; }
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  h->comm_stream = nullptr;
+  for (DevBuf* b : {&h->d_dir_mine, &h->d_dir_all, &h->d_plane_send, &h->d_plane_recv, &h->d_nplane_out, &h->d_nplane_in})
+    b->release();
+  h->world = 1; h->rank = 0;
+  return ZM_OK;
+}
+
+int zm_comm_init(zm_handle* h, const void* id_collectives, const void* id_neighbours, int world, int rank) {
+  if (!h || !id_collectives || !id_neighbours || world < 1 || rank < 0 || rank >= world) return ZM_ERR_INVALID;
+  const NcclApi& N = nccl_api();
+  if (!N.ok) return fail(h, ZM_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  zm_comm_destroy(h);
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  ncclUniqueId a, b;
+  memcpy(&a, id_collectives, 128);
+  memcpy(&b, id_neighbours, 128);
+  ZM_NCCL(h, N.CommInitRank(&h->comm, world, a, rank));
+  ZM_NCCL(h, N.CommInitRank(&h->comm_p2p, world, b, rank));
+  ZM_CUDA(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev_comm) ZM_CUDA(h, cudaEventCreate(&ev));
+  h->world = world;
+  h->rank = rank;
+  return ZM_OK;
+}
+
+int zm_slab_range(uint64_t full_extent, int close, int rank, int world, zm_slab* slab, uint64_t* in_lo, uint64_t* in_hi) {
+  if (!slab || world < 1 || rank < 0 || rank >= world) return ZM_ERR_INVALID;
+  const uint64_t pad = close ? 1 : 0;
+  const uint64_t ncube = full_extent + 2 * pad - 1;  // cube-origin planes of the whole (extended) volume
+  if (full_extent == 0 || (uint64_t)world > ncube) return ZM_ERR_INVALID;
+  slab->full_extent = full_extent;
+  slab->cube_lo = ncube * (uint64_t)rank / (uint64_t)world;
+  slab->cube_hi = ncube * (uint64_t)(rank + 1) / (uint64_t)world;
+  slab->last = rank == world - 1;
+  const uint64_t lo = slab->cube_lo > pad ? slab->cube_lo - pad : 0;
+  const uint64_t hi = std::min<uint64_t>(slab->cube_hi - pad, full_extent - 1) + 1;
+  slab->buf_lo = lo;
+  if (in_lo) *in_lo = lo;
+  if (in_hi) *in_hi = hi;
+  return ZM_OK;
+}
+
+int zm_slab_step(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz, int c_order,
+                 int close, int mem_kind, uint64_t full_extent, uint64_t buf_lo, int finalize, int normals,
+                 int voxel_centered, const float centering_offset[3]) {
+  if (!h) return ZM_ERR_INVALID;
+  if (!h->comm) return fail(h, ZM_ERR_STATE, "zm_comm_init has not been called");
+  const NcclApi& N = nccl_api();
+  zm_slab slab{};
+  if (zm_slab_range(full_extent, close, h->rank, h->world, &slab, nullptr, nullptr) != ZM_OK)
+    return fail(h, ZM_ERR_INVALID, "more shards than cube planes");
+  slab.buf_lo = buf_lo;
+  const bool last = slab.last != 0;
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    int rc = run_mesh(h, labels, label_bytes, sx, sy, sz, c_order, close, mem_kind, &slab);
+    h->failed = rc != ZM_OK;
+    if (rc != ZM_OK) return rc;
+    cudaStream_t st = h->stream;
+    // 1. label directories: export -> all-gather -> per-label offsets, all on the handle's stream
+    ZM_CUDA(h, cudaEventRecord(h->ev_comm[0], st));
+    const uint64_t cap = h->dir_cap, words = 2 * (1 + cap);
+    ZM_CUDA(h, h->d_dir_mine.ensure(words * 8));
+    ZM_CUDA(h, h->d_dir_all.ensure(words * 8 * (uint64_t)h->world));
+    rc = zm_export_directory(h, h->d_dir_mine.as<uint64_t>(), cap);
+    if (rc != ZM_OK) return rc;
+    ZM_NCCL(h, N.AllGather(h->d_dir_mine.p, h->d_dir_all.p, words, ncclUint64, h->comm, st));
+    rc = zm_import_directories(h, h->d_dir_all.as<uint64_t>(), (uint32_t)h->world, (uint32_t)h->rank, cap);
+    if (rc != ZM_OK) return rc;
+    // 2. boundary plane: rank r + 1 -> rank r (64 MiB for c5: 0.14 ms over NVLink).  On the handle's own stream: pass 2
+    //    is a persistent kernel that fills every SM, so a transfer queued beside it on a second stream does not start
+    //    before pass 2 retires (measured: 0.95 ms lost per step at 8 GPUs) -- it runs first instead.
+    const uint64_t n = zm_plane_elems(h);
+    if (h->rank > 0) {
+      ZM_CUDA(h, h->d_plane_send.ensure(n * 4));
+      rc = zm_export_plane(h, h->d_plane_send.as<uint32_t>());
+      if (rc != ZM_OK) return rc;
+    }
+    if (!last) ZM_CUDA(h, h->d_plane_recv.ensure(n * 4));
+    ZM_NCCL(h, N.GroupStart());
+    if (h->rank > 0) ZM_NCCL(h, N.Send(h->d_plane_send.p, n, ncclUint32, h->rank - 1, h->comm_p2p, st));
+    if (!last) ZM_NCCL(h, N.Recv(h->d_plane_recv.p, n, ncclUint32, h->rank + 1, h->comm_p2p, st));
+    ZM_NCCL(h, N.GroupEnd());
+    h->foreign = last ? nullptr : h->d_plane_recv.as<uint32_t>();
+    ZM_CUDA(h, cudaEventRecord(h->ev_comm[1], st));
+    const bool pass2 = finalize || normals;
+    if (pass2 && !last) {
+      if (normals) {
+        ZM_CUDA(h, h->d_nplane_out.ensure(n * 12));
+        h->nplane_out = h->d_nplane_out.as<float>();
+      }
+      // all tiles below the top layer with the cheaper kernel variant (they never look at the boundary plane)
+      rc = do_finalize(h, normals, voxel_centered, 0, centering_offset, true);
+      if (rc != ZM_OK) return rc;
+    }
+    if (!pass2) {  // (the caller finalizes later: only the overflow check is left, it needs the host)
+      ZM_CUDA(h, cudaMemcpyAsync(&h->h_ctl->flags, &h->d_ctl.as<Control>()->flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      ZM_CUDA(h, cudaStreamSynchronize(st));
+      if (h->h_ctl->flags & FLAG_DIR) { h->dir_cap *= 4; continue; }
+      return ZM_OK;
+    }
+    rc = do_finalize(h, normals, voxel_centered, 0, centering_offset);
+    if (rc == ZM_ERR_STATE && (h->h_ctl->flags & FLAG_DIR)) {  // every shard sees every directory size: all of them repeat
+      h->dir_cap *= 4;
+      continue;
+    }
+    if (rc != ZM_OK) return rc;
+    cudaEventElapsedTime(&h->stats.ms_exchange, h->ev_comm[0], h->ev_comm[1]);  // (waits for the slowest rank included)
+    if (normals) {
+      // 3. normal contributions of the top cube layer to the next shard's first-plane vertices: rank r -> r + 1
+      if (h->rank > 0) ZM_CUDA(h, h->d_nplane_in.ensure(n * 12));
+      ZM_NCCL(h, N.GroupStart());
+      if (!last) ZM_NCCL(h, N.Send(h->d_nplane_out.p, n * 3, ncclFloat32, h->rank + 1, h->comm_p2p, st));
+      if (h->rank > 0) ZM_NCCL(h, N.Recv(h->d_nplane_in.p, n * 3, ncclFloat32, h->rank - 1, h->comm_p2p, st));
+      ZM_NCCL(h, N.GroupEnd());
+      if (h->rank > 0) {
+        rc = zm_add_normal_plane(h, h->d_nplane_in.as<float>());
+        if (rc != ZM_OK) return rc;
+      }
+      rc = zm_finish_normals(h);
+      if (rc != ZM_OK) return rc;
+    }
+    return ZM_OK;
+  }
+  return fail(h, ZM_ERR_UNSUPPORTED, "slab step: the label directory exchange did not converge");
 }
 
 int zm_sync(zm_handle* h) {

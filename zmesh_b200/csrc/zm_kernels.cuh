@@ -1655,7 +1655,9 @@ __device__ __forceinline__ void mbar_arrive(u64* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <bool CO, bool NORMALS, bool SLAB>
+// SLAB: 0 unsharded; 1 slab shard, tiles that never touch the next shard's boundary plane (face indices get the label's
+// cross-shard offset); 2 slab shard, tiles whose cubes may reference that plane (the top tile layer)
+template <bool CO, bool NORMALS, int SLAB>
 __global__ void __launch_bounds__(EMIT_THREADS, NORMALS ? 3 : ZM_EMIT_CTAS)
 k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2Args a) {
   constexpr uint32_t FULL = 0xffffffffu;
@@ -1693,46 +1695,58 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
 
   if (warp == EMIT_NC) {
     // ================= producer warp =================
-    TileHdr hn;
-    hn.tile = 0; hn.nlab = 0; hn.tlbase = 0;
-    if (lane == 0) hn = load_hdr(a.hdr + first);
+    // The CTA's headers are read 32 at a time (lane l: tile first + (base + l) * G; the next batch is in flight while
+    // the current one is published), filtered by tile layer for the split launches of slab shards, and the ones that
+    // pass are published one by one.
     uint32_t pub = 0;  // tiles published so far (the consumers see exactly these, then the end marker)
-    for (uint32_t it = 0; it < ntile; ++it) {
-      const uint32_t tilev = __shfl_sync(FULL, hn.tile, 0);
-      const bool pass = !SLAB || a.layer_mode == 0u || ((tilev >= a.top_tile_lo) == (a.layer_mode == 2u));
-      if (!pass) {
-        if (lane == 0 && it + 1 < ntile) hn = load_hdr(a.hdr + first + (size_t)(it + 1) * G);
-        continue;
-      }
-      const int s = pub % EMIT_ST;
-      const uint32_t k = pub / EMIT_ST;  // k-th use of stage s
-      ++pub;
-      if (k > 0) mbar_wait(&empty[s], (k - 1) & 1u);  // every consumer warp has released the stage
-      if (lane == 0) {
-        s_hdr[s] = hn;
-        uint32_t b = hn.tile;
-        const uint32_t tf = b % vp.ntf;
-        b /= vp.ntf;
-        // The region buffers are only ever READ through the generic proxy and those reads are ordered before
-        // this refill by the `empty` mbarrier, so no proxy fence is needed.
-        mbar_expect_tx(&full[s], (uint32_t)(RGN_ROWS * RGN_WORDS * 4));
-        tma_load_3d(R[s], &rmap, &full[s], (int)(tf * RI_WORDS), (int)((b % vp.ntm) * TM), (int)((b / vp.ntm) * TS));
-      }
-      const uint32_t nlab = __shfl_sync(FULL, (uint32_t)hn.nlab, 0), tlbase = __shfl_sync(FULL, hn.tlbase, 0);
-      if (lane == 0 && it + 1 < ntile) hn = load_hdr(a.hdr + first + (size_t)(it + 1) * G);  // next header in flight
-      for (uint32_t j = lane; j < nlab && j < (uint32_t)TLC; j += 32) tlss[s][j] = a.tl[tlbase + j];
-      mbar_wait(&full[s], k & 1u);  // every lane waits itself: the TMA writes are visible to it afterwards
-      for (int e = lane; e < RGN_ROWS * 2; e += 32) {
-        const uint32_t* seg = R[s] + e * RI_WORDS;
-        uint32_t run = seg[6];
-#pragma unroll
-        for (int p = 0; p < 6; ++p) {
-          rbs[s][e * RI_WORDS + p] = run;
-          run += __popc(seg[p]);
+    union HdrWords { uint4 q[2]; TileHdr h; };
+    HdrWords nxt;
+    nxt.q[0] = nxt.q[1] = make_uint4(0u, 0u, 0u, 0u);
+    if ((uint32_t)lane < ntile) nxt.h = load_hdr(a.hdr + first + (size_t)lane * G);
+    for (uint32_t base = 0; base < ntile; base += 32) {
+      const HdrWords cur = nxt;
+      const bool have = base + lane < ntile;
+      if (base + 32 + lane < ntile) nxt.h = load_hdr(a.hdr + first + (size_t)(base + 32 + lane) * G);
+      const bool pass = have && (SLAB == 0 || a.layer_mode == 0u || ((cur.h.tile >= a.top_tile_lo) == (a.layer_mode == 2u)));
+      uint32_t todo = __ballot_sync(FULL, pass);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        HdrWords hw;  // every lane holds the header of lane `src`
+        hw.q[0] = make_uint4(__shfl_sync(FULL, cur.q[0].x, src), __shfl_sync(FULL, cur.q[0].y, src),
+                             __shfl_sync(FULL, cur.q[0].z, src), __shfl_sync(FULL, cur.q[0].w, src));
+        hw.q[1] = make_uint4(__shfl_sync(FULL, cur.q[1].x, src), __shfl_sync(FULL, cur.q[1].y, src),
+                             __shfl_sync(FULL, cur.q[1].z, src), __shfl_sync(FULL, cur.q[1].w, src));
+        const TileHdr& hn = hw.h;
+        const int s = pub % EMIT_ST;
+        const uint32_t k = pub / EMIT_ST;  // k-th use of stage s
+        ++pub;
+        if (k > 0) mbar_wait(&empty[s], (k - 1) & 1u);  // every consumer warp has released the stage
+        if (lane == 0) {
+          s_hdr[s] = hn;
+          uint32_t b = hn.tile;
+          const uint32_t tf = b % vp.ntf;
+          b /= vp.ntf;
+          // The region buffers are only ever READ through the generic proxy and those reads are ordered before
+          // this refill by the `empty` mbarrier, so no proxy fence is needed.
+          mbar_expect_tx(&full[s], (uint32_t)(RGN_ROWS * RGN_WORDS * 4));
+          tma_load_3d(R[s], &rmap, &full[s], (int)(tf * RI_WORDS), (int)((b % vp.ntm) * TM), (int)((b / vp.ntm) * TS));
         }
+        const uint32_t nlab = hn.nlab, tlbase = hn.tlbase;
+        for (uint32_t j = lane; j < nlab && j < (uint32_t)TLC; j += 32) tlss[s][j] = a.tl[tlbase + j];
+        mbar_wait(&full[s], k & 1u);  // every lane waits itself: the TMA writes are visible to it afterwards
+        for (int e = lane; e < RGN_ROWS * 2; e += 32) {
+          const uint32_t* seg = R[s] + e * RI_WORDS;
+          uint32_t run = seg[6];
+#pragma unroll
+          for (int p = 0; p < 6; ++p) {
+            rbs[s][e * RI_WORDS + p] = run;
+            run += __popc(seg[p]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[s]);  // (release: header, tl cache and slot bases are visible to the waiters)
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ready[s]);  // (release: header, tl cache and slot bases are visible to the waiters)
     }
     {  // end marker: a header without a tile
       const int s = pub % EMIT_ST;
@@ -1771,7 +1785,7 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
     const TLEntry* const tls = tlss[s];
     // slab sharding: region rows [ftop9, ftop9 + RM) lie on the plane owned by the next shard
     uint32_t ftop9 = 0xFFFFu;
-    if (SLAB && vp.Es_own < vp.Es && vp.Es_own >= es0 && vp.Es_own - es0 < (uint32_t)RS) ftop9 = (vp.Es_own - es0) * RM;
+    if (SLAB == 2 && vp.Es_own < vp.Es && vp.Es_own >= es0 && vp.Es_own - es0 < (uint32_t)RS) ftop9 = (vp.Es_own - es0) * RM;
 
     // ---- faces ----
     if (a.write_faces || NORMALS) {
@@ -1818,7 +1832,7 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
             const uint32_t uw = u0 + (en & 0xFFu);  // word of (row, plane) in the first segment
             const uint32_t rr = uw >> 4;
             // slot = 2*axis + side; side 0: the owner (lower) voxel carries the label, 1: the upper one
-            if (SLAB && rr - ftop9 < (uint32_t)RM) {
+            if (SLAB == 2 && rr - ftop9 < (uint32_t)RM) {
               const uint32_t fs = 4u * ((em0 + rr - ftop9) * vp.Efp + ef0 + lfx) + slot;  // (zm_mesh_slab rejects planes of 2^32 or more slots)
               vi[c] = __ldg(a.foreign + fs);
               if (NORMALS) fslot[c] = fs;
@@ -1841,7 +1855,7 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
             float* d0 = nb + 3ull * (vi[0] - voff);
             float* d1 = nb + 3ull * (vi[1] - voff);
             float* d2 = nb + 3ull * (vi[2] - voff);
-            if (SLAB) {  // vertices of the next shard: accumulate in the plane buffer that is sent to it
+            if (SLAB == 2) {  // vertices of the next shard: accumulate in the plane buffer that is sent to it
               if (fslot[0] != 0xFFFFFFFFu) d0 = a.fnormals + 3ull * fslot[0];
               if (fslot[1] != 0xFFFFFFFFu) d1 = a.fnormals + 3ull * fslot[1];
               if (fslot[2] != 0xFFFFFFFFu) d2 = a.fnormals + 3ull * fslot[2];

@@ -205,6 +205,46 @@ class Mesher:
     self._check(self._lib.zm_set_label_offsets(self._h, labels.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                offsets.ctypes.data_as(C.POINTER(C.c_uint32)), labels.size))
 
+  # native multi-GPU step: NCCL driven from the C++ layer (zm_comm_init / zm_slab_step)
+  @staticmethod
+  def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    lib = _lib.load()
+    rc = lib.zm_nccl_unique_id(buf)
+    if rc != 0:
+      msg = lib.zm_last_error(None)
+      raise RuntimeError(f"zmesh_b200: {msg.decode() if msg else rc}")
+    return buf.raw
+
+  def comm_init(self, id_collectives: bytes, id_neighbours: bytes, world: int, rank: int):
+    self._check(self._lib.zm_comm_init(self._h, id_collectives, id_neighbours, int(world), int(rank)))
+
+  def slab_step(self, data, full_extent: int, buf_lo: int, close=False, finalize=True, normals=False, voxel_centered=False):
+    """One whole slab step on this rank (see zm_slab_step): `data` holds the input planes [buf_lo, buf_lo + n) along the
+    slowest memory axis (numpy array, or a device array exposing __cuda_array_interface__)."""
+    res = _f3(self._voxel_res)
+    self._stage = None
+    self._erased = set()
+    self._check(self._lib.zm_set_resolution(self._h, res.ctypes.data_as(C.POINTER(C.c_float))))
+    cai = getattr(data, "__cuda_array_interface__", None)
+    if cai is not None and not isinstance(data, np.ndarray):
+      ptr, nbytes, shape, c_order = self._device_view(data, cai)
+      mem_kind = 1
+    else:
+      data = np.asarray(data)
+      nbytes = data.dtype.itemsize
+      if nbytes not in (1, 2, 4, 8):
+        raise TypeError(f"unsupported label dtype {data.dtype}")
+      data = as_volume3d(data, bool(close))
+      shape = tuple(int(x) for x in data.shape)
+      c_order = 1 if data.flags.c_contiguous else 0
+      ptr, mem_kind = data.ctypes.data, 0
+    self._max_label = (1 << (8 * nbytes)) - 1
+    off = _f3(self._voxel_res)
+    self._check(self._lib.zm_slab_step(self._h, C.c_void_p(ptr), nbytes, shape[0], shape[1], shape[2], c_order,
+                                       1 if close else 0, mem_kind, int(full_extent), int(buf_lo), int(bool(finalize)),
+                                       int(bool(normals)), int(bool(voxel_centered)), off.ctypes.data_as(C.POINTER(C.c_float))))
+
   def export_directory(self, dst_device_ptr: int, capacity: int):
     """Device-side directory exchange (no host round trip): see zm_export_directory."""
     self._check(self._lib.zm_export_directory(self._h, C.c_void_p(int(dst_device_ptr)), int(capacity)))
@@ -240,7 +280,9 @@ class Mesher:
     """The caller-owned stream set by set_stream (integer cudaStream_t), or None for the handle's own."""
     return getattr(self, "_user_stream", None)
 
-  def _mesh_device(self, obj, cai, close: bool):
+  def _device_view(self, obj, cai):
+    """(pointer, label bytes, (sx, sy, sz), c_order) of a device array; the mesher's stream is ordered after the work
+    that produced it."""
     shape = tuple(int(s) for s in cai["shape"])
     if len(shape) < 3:
       raise IndexError("tuple index out of range")
@@ -262,7 +304,6 @@ class Mesher:
     else:
       raise ValueError("device arrays must be C- or Fortran-contiguous")
     ptr = int(cai["data"][0])
-    self._max_label = (1 << (8 * nbytes)) - 1
     # order the mesher's stream after the work that produced the array: the stream the interface names (v3), else
     # torch's current stream for a torch tensor, else the legacy default stream
     producer = cai.get("stream")
@@ -273,6 +314,11 @@ class Mesher:
       else:
         producer = 1
     self._check(self._lib.zm_wait_stream(self._h, C.c_void_p(int(producer)) if producer else None))
+    return ptr, nbytes, s3, c_order
+
+  def _mesh_device(self, obj, cai, close: bool):
+    ptr, nbytes, s3, c_order = self._device_view(obj, cai)
+    self._max_label = (1 << (8 * nbytes)) - 1
     self._check(self._call_mesh(ptr, nbytes, s3, c_order, close, 1))
 
   def ids(self):

@@ -119,13 +119,22 @@ class ShardedMesher:
   """One instance per rank.  mesh_slab() runs the rank's share of the path and the exchanges;
   afterwards the rank holds its parts of every label (device resident until fetched)."""
 
-  def __init__(self, voxel_res, device: int, group=None):
+  def __init__(self, voxel_res, device: int, group=None, native: bool = True):
+    """native: run the whole step in the C++ layer with its own NCCL communicators (zm_slab_step; torch.distributed
+    is only used once, to hand out the communicator ids); False: the step is driven from Python over torch.distributed
+    (the same kernels and exchanges, more host time per step)."""
     import torch.distributed as dist
     self.group = group
     self.rank = dist.get_rank(group)
     self.world = dist.get_world_size(group)
     self.device = int(device)
     self.mesher = Mesher(voxel_res, device=self.device)
+    self.native = False
+    if native and dist.get_backend(group) == "nccl":
+      ids = [Mesher.nccl_unique_id(), Mesher.nccl_unique_id()] if self.rank == 0 else [None, None]
+      dist.broadcast_object_list(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+      self.mesher.comm_init(ids[0], ids[1], self.world, self.rank)
+      self.native = True
     self._plane_send = None
     self._plane_recv = None
     self._nplane_out = None
@@ -144,6 +153,9 @@ class ShardedMesher:
     import torch.distributed as dist
     cube_lo, cube_hi, in_lo, in_hi, last = self.planes(full_extent, close)
     m = self.mesher
+    if self.native:
+      m.slab_step(data, full_extent, buf_lo, close=close, finalize=finalize, normals=normals, voxel_centered=voxel_centered)
+      return m.finalize(normals=normals, voxel_centered=voxel_centered) if (finalize or normals) else None
     tm = self._timer()
     m.mesh_slab(data, full_extent, buf_lo, cube_lo, cube_hi, last, close=close)
     tm("pass1")
