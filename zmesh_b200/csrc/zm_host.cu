@@ -91,7 +91,11 @@ struct zm_handle {
   float* nplane_out = nullptr;        // borrowed: normal contributions to the next shard's first-plane vertices
   uint64_t capL = 0;
   zm::Control* h_ctl = nullptr;  // pinned
-  std::vector<uint64_t> h_list;
+  uint64_t* h_list = nullptr;  // pinned, grow-only: (label, nV, nT) per label, copied asynchronously by zm_mesh
+  size_t h_list_cap = 0;
+  uint64_t nlabels = 0;
+  bool dir_pending = false;    // the host-side directory (recs / index / sorted_ids) has not been built from h_list yet
+  cudaEvent_t ev_list = nullptr;
 
   // what pass 2 needs to know about the meshed volume
   zm::VolParams vp{};
@@ -256,6 +260,8 @@ void drop_results(zm_handle* h) {
   h->recs.clear();
   h->index.clear();
   h->sorted_ids.clear();
+  h->dir_pending = false;
+  h->nlabels = 0;
   h->bulk_labels.clear();
   h->bulk_voff.clear();
   h->bulk_foff.clear();
@@ -424,34 +430,23 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   if (Ttot != ctl.cur_tri)
     return fail(h, ZM_ERR_UNSUPPORTED, "a label has more than 2^32-1 faces in one call; shard the volume");
 
+  // The label directory crosses PCIe asynchronously; the host-side structures are built from it on first use
+  // (ensure_directory) -- by pass 2 while its kernel runs, so the GPU never waits for the host's hash map and sort.
   if (nlabels) {
-    h->h_list.resize((size_t)nlabels * 3);
-    ZM_CUDA(h, cudaMemcpyAsync(h->h_list.data(), h->d_list.p, (size_t)nlabels * 24, cudaMemcpyDeviceToHost, st));
+    if ((size_t)nlabels * 3 > h->h_list_cap) {
+      if (h->h_list) cudaFreeHost(h->h_list);
+      h->h_list = nullptr;
+      h->h_list_cap = 0;
+      const size_t want = (size_t)nlabels * 3 + 3072;
+      ZM_CUDA(h, cudaHostAlloc((void**)&h->h_list, want * 8, cudaHostAllocDefault));
+      h->h_list_cap = want;
+    }
+    ZM_CUDA(h, cudaMemcpyAsync(h->h_list, h->d_list.p, (size_t)nlabels * 24, cudaMemcpyDeviceToHost, st));
   }
   ZM_CUDA(h, cudaEventRecord(h->ev[4], st));
-  ZM_CUDA(h, cudaStreamSynchronize(st));
-
-  // host-side label directory (storage order = table order; offsets are running sums)
-  h->recs.resize((size_t)nlabels);
-  h->index.reserve((size_t)nlabels * 2);
-  uint64_t vo = 0, fo = 0;
-  for (size_t i = 0; i < (size_t)nlabels; ++i) {
-    LabelRec& r = h->recs[i];
-    r.label = h->h_list[3 * i];
-    r.nv = h->h_list[3 * i + 1];
-    r.nt = h->h_list[3 * i + 2];
-    r.voff = vo;
-    r.foff = fo;
-    r.erased = false;
-    vo += r.nv;
-    fo += r.nt;
-    h->index.emplace(r.label, (uint32_t)i);
-  }
-  if (vo != Vtot || fo != Ttot) return fail(h, ZM_ERR_CUDA, "internal: label directory does not add up");
-  h->sorted_ids.reserve((size_t)nlabels);
-  for (const LabelRec& r : h->recs)
-    if (r.nt) h->sorted_ids.push_back(r.label);
-  std::sort(h->sorted_ids.begin(), h->sorted_ids.end());
+  ZM_CUDA(h, cudaEventRecord(h->ev_list, st));
+  h->nlabels = nlabels;
+  h->dir_pending = true;
   h->Vtot = Vtot;
   h->Ttot = Ttot;
   h->vp = vp;
@@ -460,7 +455,7 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   h->capL = capL;
 
   h->has_result = true;
-  h->stats.n_labels = h->sorted_ids.size();
+  h->stats.n_labels = nlabels;  // (labels with vertices; ensure_directory replaces it by the number of ids = labels with faces)
   h->stats.n_vertices = Vtot;
   h->stats.n_faces = Ttot;
   h->stats.n_records = ctl.cur_rec;
@@ -474,11 +469,44 @@ int run_mesh(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uin
   cudaEventElapsedTime(&h->stats.ms_h2d, h->ev[0], h->ev[1]);
   cudaEventElapsedTime(&h->stats.ms_classify, h->ev[1], h->ev[2]);
   cudaEventElapsedTime(&h->stats.ms_scan, h->ev[2], h->ev[3]);
-  cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[4]);
+  cudaEventElapsedTime(&h->stats.ms_total, h->ev[0], h->ev[3]);
   // let the capacity guesses track the data (next call of a similar volume needs one attempt)
   h->perm_ratio = std::max(0.02, std::min(6.5, 1.25 * (double)ctl.cur_perm / (double)nvox));
   h->rec_ratio = std::max(0.02, std::min(8.5, 1.25 * (double)ctl.cur_rec / (double)nvox));
   h->tl_ratio = std::max(0.002, std::min(2.0, 1.25 * (double)ctl.cur_tl / (double)nvox));
+  return ZM_OK;
+}
+
+// host-side label directory (storage order = table order; offsets are running sums), built on first use
+int ensure_directory(zm_handle* h) {
+  if (!h->dir_pending) return ZM_OK;
+  ZM_CUDA(h, cudaEventSynchronize(h->ev_list));
+  h->dir_pending = false;
+  const size_t nlabels = (size_t)h->nlabels;
+  h->recs.resize(nlabels);
+  h->index.reserve(nlabels * 2);
+  uint64_t vo = 0, fo = 0;
+  for (size_t i = 0; i < nlabels; ++i) {
+    LabelRec& r = h->recs[i];
+    r.label = h->h_list[3 * i];
+    r.nv = h->h_list[3 * i + 1];
+    r.nt = h->h_list[3 * i + 2];
+    r.voff = vo;
+    r.foff = fo;
+    r.erased = false;
+    vo += r.nv;
+    fo += r.nt;
+    h->index.emplace(r.label, (uint32_t)i);
+  }
+  if (vo != h->Vtot || fo != h->Ttot) {
+    h->failed = true;
+    return fail(h, ZM_ERR_CUDA, "internal: label directory does not add up");
+  }
+  h->sorted_ids.reserve(nlabels);
+  for (const LabelRec& r : h->recs)
+    if (r.nt) h->sorted_ids.push_back(r.label);
+  std::sort(h->sorted_ids.begin(), h->sorted_ids.end());
+  h->stats.n_labels = h->sorted_ids.size();
   return ZM_OK;
 }
 
@@ -587,6 +615,10 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     }
   }
   ZM_CUDA(h, cudaEventRecord(h->ev[7], st));
+  {  // (host work overlapped with pass 2)
+    const int rc = ensure_directory(h);
+    if (rc != ZM_OK) return rc;
+  }
   if (h->dir_exchange)  // (device-side directory exchange: its overflow flag travels with this synchronisation)
     ZM_CUDA(h, cudaMemcpyAsync(&h->h_ctl->flags, &h->d_ctl.as<Control>()->flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
   ZM_CUDA(h, cudaStreamSynchronize(st));
@@ -702,6 +734,7 @@ int zm_create(const float resolution[3], int device, zm_handle** out) {
   for (auto& ev : h->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail("cudaEventCreate", e);
   if ((e = cudaHostAlloc((void**)&h->h_ctl, sizeof(zm::Control), cudaHostAllocDefault)) != cudaSuccess) return bail("cudaHostAlloc", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_list, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
   int rc = prepare_device(h);
   if (rc != ZM_OK) {
     g_create_error = h->err;
@@ -722,6 +755,8 @@ void zm_destroy(zm_handle* h) {
                     &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals, &h->d_voff, &h->d_tmpA, &h->d_tmpB})
     b->release();
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->h_list) cudaFreeHost(h->h_list);
+  if (h->ev_list) cudaEventDestroy(h->ev_list);
   for (auto& ev : h->ev)
     if (ev) cudaEventDestroy(ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -795,6 +830,7 @@ int zm_mesh_slab(zm_handle* h, const void* labels, int label_bytes, uint64_t sx,
 
 int zm_directory(zm_handle* h, uint64_t* labels, uint64_t* n_vertices, uint64_t* n_faces, uint64_t capacity) {
   if (!h) return ZM_ERR_INVALID;
+  if (ensure_directory(h) != ZM_OK) return ZM_ERR_CUDA;
   const uint64_t n = std::min<uint64_t>(capacity, h->recs.size());
   for (uint64_t i = 0; i < n; ++i) {
     if (labels) labels[i] = h->recs[i].label;
@@ -804,7 +840,7 @@ int zm_directory(zm_handle* h, uint64_t* labels, uint64_t* n_vertices, uint64_t*
   return ZM_OK;
 }
 
-uint64_t zm_num_directory(zm_handle* h) { return h ? h->recs.size() : 0; }
+uint64_t zm_num_directory(zm_handle* h) { return h ? h->nlabels : 0; }
 
 int zm_set_label_offsets(zm_handle* h, const uint64_t* labels, const uint32_t* offsets, uint64_t n) {
   if (!h || (n && (!labels || !offsets))) return ZM_ERR_INVALID;
@@ -834,11 +870,11 @@ int zm_export_directory(zm_handle* h, uint64_t* dst_device, uint64_t capacity) {
   if (!h || !dst_device) return ZM_ERR_INVALID;
   if (!h->has_result) return fail(h, ZM_ERR_STATE, "zm_mesh has not been called");
   ZM_CUDA(h, cudaSetDevice(h->device));
-  if (!h->n_work && h->recs.empty()) {  // nothing meshed on this shard (degenerate slab): an empty directory
+  if (!h->n_work && h->nlabels == 0) {  // nothing meshed on this shard (degenerate slab): an empty directory
     ZM_CUDA(h, cudaMemsetAsync(dst_device, 0, 16, h->stream));
     return ZM_OK;
   }
-  k_export_directory<<<grid_for(h->recs.size() + 1, 256), 256, 0, h->stream>>>(h->d_list.as<u64>(), h->d_ctl.as<Control>(),
+  k_export_directory<<<grid_for(h->nlabels + 1, 256), 256, 0, h->stream>>>(h->d_list.as<u64>(), h->d_ctl.as<Control>(),
                                                                                (u64*)dst_device, capacity);
   ZM_CUDA(h, cudaGetLastError());
   return ZM_OK;
@@ -923,10 +959,14 @@ int zm_finish_normals(zm_handle* h) {
   return ZM_OK;
 }
 
-uint64_t zm_num_ids(zm_handle* h) { return h ? h->sorted_ids.size() : 0; }
+uint64_t zm_num_ids(zm_handle* h) {
+  if (!h || ensure_directory(h) != ZM_OK) return 0;
+  return h->sorted_ids.size();
+}
 
 int zm_ids(zm_handle* h, uint64_t* out, uint64_t capacity) {
   if (!h || (!out && capacity)) return ZM_ERR_INVALID;
+  if (ensure_directory(h) != ZM_OK) return ZM_ERR_CUDA;
   uint64_t n = std::min<uint64_t>(capacity, h->sorted_ids.size());
   if (n) memcpy(out, h->sorted_ids.data(), n * sizeof(uint64_t));
   return ZM_OK;
@@ -938,6 +978,7 @@ int zm_get_counts(zm_handle* h, uint64_t label, uint64_t* nv, uint64_t* nf) {
   // (before the first zm_mesh the handle answers like an empty volume: the reference's Mesher.__init__ builds an
   // empty Mesher6464, zmesh/_zmesh.pyx:442-444)
   if (h->failed) return fail(h, ZM_ERR_STATE, "the last zm_mesh failed; mesh again before reading results");
+  if (ensure_directory(h) != ZM_OK) return ZM_ERR_CUDA;
   auto it = h->index.find(label);
   if (it == h->index.end() || h->recs[it->second].erased) return ZM_OK;
   *nv = h->recs[it->second].nv;
@@ -949,6 +990,7 @@ int zm_get(zm_handle* h, uint64_t label, int normals, int voxel_centered, int tr
            const float centering_offset[3], float* vertices, uint32_t* faces, float* normals_out) {
   if (!h) return ZM_ERR_INVALID;
   if (h->failed) return fail(h, ZM_ERR_STATE, "the last zm_mesh failed; mesh again before reading results");
+  if (ensure_directory(h) != ZM_OK) return ZM_ERR_CUDA;
   auto it = h->index.find(label);
   if (it == h->index.end() || h->recs[it->second].erased) return ZM_OK;  // empty mesh
   const LabelRec& r = h->recs[it->second];
@@ -970,6 +1012,7 @@ int zm_get(zm_handle* h, uint64_t label, int normals, int voxel_centered, int tr
 int zm_erase(zm_handle* h, uint64_t label, int* existed) {
   if (!h) return ZM_ERR_INVALID;
   int ex = 0;
+  if (ensure_directory(h) != ZM_OK) return ZM_ERR_CUDA;
   auto it = h->index.find(label);
   if (it != h->index.end() && !h->recs[it->second].erased && h->recs[it->second].nt) {
     h->recs[it->second].erased = true;
@@ -999,6 +1042,8 @@ int zm_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
   int rc = do_finalize(h, normals, voxel_centered, transpose, centering_offset);
   if (rc != ZM_OK) return rc;
   if (view) {
+    rc = ensure_directory(h);
+    if (rc != ZM_OK) return rc;
     if (h->bulk_labels.size() != h->recs.size() || h->bulk_voff.empty()) {
       h->bulk_labels.clear(); h->bulk_voff.clear(); h->bulk_foff.clear();
       for (const LabelRec& r : h->recs) {
