@@ -410,3 +410,81 @@ def test_config4_full_size_properties(Mesher):
   for i in range(0, len(labels), 41):
     ff = f[bulk["foff"][i]:bulk["foff"][i + 1]]
     assert int(ff.max()) == nv[i] - 1 and len(np.unique(ff)) == nv[i], int(labels[i])
+
+
+def _reference_kind():
+  from oracle import oracle as O
+  return "reference" if O.have_reference() else "port"
+
+
+def test_config3_full_size(Mesher):
+  """BASELINE config 3 at its stated size (perf.py:68-77: default_rng(0).integers(0, 1000), 512^3 uint32, C order): every
+  tile overflows the per-tile staging and goes through the dense kernel.  Checked by the per-label vertex census of
+  the WHOLE volume (V_label = axis-adjacent voxel pairs with exactly one endpoint == label) and, against the compiled
+  reference, by bit-exact meshes of 20 labels on the volume's first 24 planes meshed as a standalone volume
+  (the CPU cannot hold the full triangle soup)."""
+  vol = random_volume((512, 512, 512), 1000, np.uint32, seed=0, order="C")
+  m = Mesher((4, 4, 40))
+  m.mesh(vol)
+  st = m.stats()
+  assert st["n_dense_tiles"] > 0 and st["n_tiles"] == 64 * 64 * 16
+  want = np.zeros(1000, dtype=np.int64)
+  for ax in range(3):
+    a = np.moveaxis(vol, ax, 0)[:-1]
+    b = np.moveaxis(vol, ax, 0)[1:]
+    d = a != b
+    want += np.bincount(a[d], minlength=1000) + np.bincount(b[d], minlength=1000)
+    del a, b, d
+  bulk = m.finalize()
+  got = dict(zip(bulk["labels"].tolist(), np.diff(bulk["voff"]).tolist()))
+  assert sorted(got) == list(range(1, 1000))
+  assert all(got[lbl] == want[lbl] for lbl in range(1, 1000)), "per-label vertex census"
+  assert bulk["n_vertices"] == int(want[1:].sum())
+  m.clear()
+  # against the reference on a slab it can hold
+  slab = np.ascontiguousarray(vol[:24])
+  del vol
+  cpu = OracleMesher((4, 4, 40), _reference_kind())
+  cpu.mesh(slab)
+  m.mesh(slab)
+  ids = m.ids()
+  assert ids == sorted(cpu.ids()) and len(ids) == 999
+  for lbl in ids[::50]:
+    assert_same_mesh(m.get(lbl, normals=True), cpu.get(lbl, normals=True), NORMALS_TOL, what=f"c3 slab label {lbl}")
+
+
+def test_config5_slab_against_reference(Mesher):
+  """BASELINE config 5 (Voronoi 2048^3 uint64, pitch 128): the first 32 planes of the volume, 2048 x 2048 x 32, meshed
+  as a standalone volume by the GPU path and by the compiled reference; every label compared by its order-independent
+  fingerprint (bit-exact vertex and face sets), every 16th one also in canonical form.  (bench.py repeats the check on
+  128 planes beside its cpu_baseline; the full 68.7 GB volume is compared across GPU counts by nccl_parity.)"""
+  from oracle.oracle import multiset_digest, voronoi_volume_c
+  slab = voronoi_volume_c((2048, 2048, 32), 128, np.uint64, 0, "F", full_shape=(2048, 2048, 2048))
+  m = Mesher((4, 4, 40))
+  m.mesh(slab)
+  cpu = OracleMesher((4, 4, 40), _reference_kind())
+  cpu.mesh(slab)
+  ids = m.ids()
+  assert ids == sorted(cpu.ids()) and len(ids) > 200
+  for i, lbl in enumerate(ids):
+    g, w = m.get(lbl), cpu.get(lbl)
+    assert multiset_digest(g.vertices, g.faces) == multiset_digest(w.vertices, w.faces), f"c5 slab label {lbl}"
+    if i % 16 == 0:
+      assert_same_mesh(g, w, what=f"c5 slab label {lbl}")
+
+
+def test_config4_slab_against_reference(Mesher):
+  """BASELINE config 4 (Voronoi 1024^3 uint64, pitch 64, close=True, normals, voxel_centered) on the first 24 planes as a
+  standalone volume against the compiled reference: bit-exact vertex / face sets of every label, normals within 1e-5
+  with EQUAL NaN masks (the full-size test above can only bound the NaN share)."""
+  from oracle.oracle import voronoi_volume_c
+  slab = voronoi_volume_c((1024, 1024, 24), 64, np.uint64, 0, "F", full_shape=(1024, 1024, 1024))
+  m = Mesher((4, 4, 40))
+  m.mesh(slab, close=True)
+  cpu = OracleMesher((4, 4, 40), _reference_kind())
+  cpu.mesh(slab, close=True)
+  ids = m.ids()
+  assert ids == sorted(cpu.ids()) and len(ids) >= 256
+  for lbl in ids[::4]:
+    assert_same_mesh(m.get(lbl, normals=True, voxel_centered=True), cpu.get(lbl, normals=True, voxel_centered=True),
+                     NORMALS_TOL, what=f"c4 slab label {lbl}")
