@@ -76,6 +76,7 @@ struct zm_handle {
   DevBuf d_rowinfo, d_perm, d_vinfo, d_rec, d_tl, d_hdr, d_dense;
   // results (device)
   DevBuf d_faces, d_verts, d_normals;
+  DevBuf d_nacc;  // float4 accumulation rows of the normals (pass 2 adds one vector atomic per triangle corner)
   DevBuf d_voff, d_tmpA, d_tmpB;     // slab sharding: per-table-slot index offsets; upload scratch
   bool tl_fixed = false, have_voff = false, slab_mode = false;
   bool dir_exchange = false;  // voff came from zm_import_directories: the exchange's overflow flag is checked by finalize
@@ -572,7 +573,8 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     ZM_CUDA(h, h->d_verts.ensure((size_t)h->Vtot * 12));
     if (need_normals && !f.partial) {
       ZM_CUDA(h, h->d_normals.ensure((size_t)h->Vtot * 12));
-      ZM_CUDA(h, cudaMemsetAsync(h->d_normals.p, 0, (size_t)h->Vtot * 12, st));
+      ZM_CUDA(h, h->d_nacc.ensure((size_t)h->Vtot * 16));
+      ZM_CUDA(h, cudaMemsetAsync(h->d_nacc.p, 0, (size_t)h->Vtot * 16, st));
       if (h->slab_mode && h->nplane_out)
         ZM_CUDA(h, cudaMemsetAsync(h->nplane_out, 0, (size_t)zm_plane_elems(h) * 12, st));
     }
@@ -580,6 +582,7 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     a.faces = h->d_faces.as<uint32_t>();
     a.verts = h->d_verts.as<float>();
     a.normals = h->d_normals.as<float>();
+    a.nacc = h->d_nacc.as<float4>();
     a.r0 = h->res[0]; a.r1 = h->res[1]; a.r2 = h->res[2];
     a.c0 = o[0]; a.c1 = o[1]; a.c2 = o[2];
     a.voxel_centered = voxel_centered;
@@ -609,7 +612,7 @@ int do_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, co
     }
     ZM_CUDA(h, cudaEventRecord(h->ev[6], st));
     if (need_normals && !h->slab_mode) {  // (slab shards normalise in zm_finish_normals, after the plane exchange)
-      k_normals_normalize<<<grid_for(h->Vtot, 256), 256, 0, st>>>(h->d_normals.as<float>(), h->Vtot);
+      k_normals_normalize4<<<grid_for(h->Vtot, 256), 256, 0, st>>>(h->d_nacc.as<float4>(), h->d_normals.as<float>(), h->Vtot);
       ZM_CUDA(h, cudaGetLastError());
       ++launches;
     }
@@ -752,7 +755,7 @@ void zm_destroy(zm_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_vol, &h->d_keys, &h->d_cnt, &h->d_offV, &h->d_offT, &h->d_list, &h->d_partial, &h->d_ctl,
                     &h->d_rowinfo, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_hdr,
-                    &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals, &h->d_voff, &h->d_tmpA, &h->d_tmpB})
+                    &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals, &h->d_nacc, &h->d_voff, &h->d_tmpA, &h->d_tmpB})
     b->release();
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_list) cudaFreeHost(h->h_list);
@@ -938,6 +941,7 @@ int zm_add_normal_plane(zm_handle* h, const float* src_device) {
   ZM_CUDA(h, cudaSetDevice(h->device));
   Pass2Args a = pass2_args(h);
   a.normals = h->d_normals.as<float>();
+  a.nacc = h->d_nacc.as<float4>();
   const uint32_t grid = std::min<uint32_t>((h->n_work + NT_V / 32 - 1) / (NT_V / 32), (uint32_t)h->num_sms * 16u);
   if (h->c_order) k_import_plane_normals<true><<<grid, NT_V, 0, h->stream>>>(h->vp, a, src_device);
   else k_import_plane_normals<false><<<grid, NT_V, 0, h->stream>>>(h->vp, a, src_device);
@@ -950,7 +954,7 @@ int zm_finish_normals(zm_handle* h) {
   if (!h->has_result || !h->fin.normals_pending) return fail(h, ZM_ERR_STATE, "no pending normals on this handle");
   ZM_CUDA(h, cudaSetDevice(h->device));
   if (h->Vtot && h->n_work) {
-    k_normals_normalize<<<grid_for(h->Vtot, 256), 256, 0, h->stream>>>(h->d_normals.as<float>(), h->Vtot);
+    k_normals_normalize4<<<grid_for(h->Vtot, 256), 256, 0, h->stream>>>(h->d_nacc.as<float4>(), h->d_normals.as<float>(), h->Vtot);
     ZM_CUDA(h, cudaGetLastError());
     ZM_CUDA(h, cudaStreamSynchronize(h->stream));
   }
@@ -1030,7 +1034,7 @@ int zm_clear(zm_handle* h) {
   drop_results(h);
   h->has_result = had;  // a cleared mesher answers like an empty one (marching_cubes.hpp:184-189)
   cudaSetDevice(h->device);
-  for (DevBuf* b : {&h->d_faces, &h->d_verts, &h->d_normals, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_rowinfo,
+  for (DevBuf* b : {&h->d_faces, &h->d_verts, &h->d_normals, &h->d_nacc, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_rowinfo,
                     &h->d_vol})
     b->release();
   return ZM_OK;

@@ -914,7 +914,10 @@ __device__ __forceinline__ int tile_body(const VolParams& vp, const Pass1Args& o
     }
   }
   __syncthreads();
-  if (!S.ok1) return TILE_DONE;  // capacity guess too small: the cursors still give the exact need; host reruns
+  if (!S.ok1) {  // capacity guess too small: ALL cursors still advance, so one failed attempt gives the exact need of every buffer
+    if (tid == 0 && S.ci) atomicAdd(&o.ctl->cur_tl, (u64)S.ci);
+    return TILE_DONE;
+  }
   const uint32_t gbase = S.gbase;
   const u64 recbase = S.recbase;
   if (tid == 0) {  // tl block + work-list entry; the latency of these atomics hides behind the flush below
@@ -1524,7 +1527,9 @@ struct Pass2Args {
   const TLEntry* tl;
   uint32_t* faces;  // [T_total][3]
   float* verts;     // [V_total][3]
-  float* normals;   // [V_total][3] or null
+  float* normals;   // [V_total][3] or null (k_normals_normalize4 writes it; arbitrary-mesh path accumulates in it)
+  float4* nacc;     // [V_total] accumulation rows of pass 2: ONE 16-byte vector atomic per triangle corner instead of three
+                    // scalar ones (sm_90+: atomicAdd(float4*)); .w unused
   float r0, r1, r2;  // captured resolution
   float c0, c1, c2;  // centering offset
   uint32_t n_work;
@@ -1542,9 +1547,11 @@ __device__ __forceinline__ float len3(float x, float y, float z) {
 }
 
 // One face: n_hat = hat(cross(v1-v0, v2-v0)); N[f_k] += n_hat * |v_k - centroid|
-// (chunk_mesh.hpp:355-368; float32 op for op, accumulation order is not the reference's).
+// (chunk_mesh.hpp:355-368; float32 op for op, accumulation order is not the reference's).  A destination is a row of
+// three floats (scalar atomics) or, vec[k] = true, a 16-byte aligned float4 row (one vector atomic).
 __device__ __forceinline__ void face_normal_scatter(const float v0[3], const float v1[3], const float v2[3],
-                                                    float* d0, float* d1, float* d2) {
+                                                    float* d0, float* d1, float* d2, bool vec0 = false, bool vec1 = false,
+                                                    bool vec2 = false) {
   float c[3], e1[3], e2[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -1559,12 +1566,18 @@ __device__ __forceinline__ void face_normal_scatter(const float v0[3], const flo
   if (l != 1.0f) { n0 = __fdiv_rn(n0, l); n1 = __fdiv_rn(n1, l); n2 = __fdiv_rn(n2, l); }
   const float* vv[3] = {v0, v1, v2};
   float* dd[3] = {d0, d1, d2};
+  const bool vec[3] = {vec0, vec1, vec2};
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float w = len3(__fsub_rn(vv[k][0], c[0]), __fsub_rn(vv[k][1], c[1]), __fsub_rn(vv[k][2], c[2]));
-    atomicAdd(dd[k] + 0, __fmul_rn(n0, w));
-    atomicAdd(dd[k] + 1, __fmul_rn(n1, w));
-    atomicAdd(dd[k] + 2, __fmul_rn(n2, w));
+    const float x = __fmul_rn(n0, w), y = __fmul_rn(n1, w), z = __fmul_rn(n2, w);
+    if (vec[k]) {
+      atomicAdd(reinterpret_cast<float4*>(dd[k]), make_float4(x, y, z, 0.0f));
+    } else {
+      atomicAdd(dd[k] + 0, x);
+      atomicAdd(dd[k] + 1, y);
+      atomicAdd(dd[k] + 2, z);
+    }
   }
 }
 
@@ -1851,18 +1864,19 @@ k_emit(const VolParams vp, const __grid_constant__ CUtensorMap rmap, const Pass2
             f[0] = vi[0]; f[1] = vi[1]; f[2] = vi[2];
           }
           if (NORMALS) {
-            float* nb = a.normals + 3ull * rv[cw][src];
-            float* d0 = nb + 3ull * (vi[0] - voff);
-            float* d1 = nb + 3ull * (vi[1] - voff);
-            float* d2 = nb + 3ull * (vi[2] - voff);
-            if (SLAB == 2) {  // vertices of the next shard: accumulate in the plane buffer that is sent to it
-              if (fslot[0] != 0xFFFFFFFFu) d0 = a.fnormals + 3ull * fslot[0];
-              if (fslot[1] != 0xFFFFFFFFu) d1 = a.fnormals + 3ull * fslot[1];
-              if (fslot[2] != 0xFFFFFFFFu) d2 = a.fnormals + 3ull * fslot[2];
+            float4* nb = a.nacc + rv[cw][src];
+            float* d0 = reinterpret_cast<float*>(nb + (vi[0] - voff));
+            float* d1 = reinterpret_cast<float*>(nb + (vi[1] - voff));
+            float* d2 = reinterpret_cast<float*>(nb + (vi[2] - voff));
+            bool q0 = true, q1 = true, q2 = true;  // float4 rows of this shard (one vector atomic each)
+            if (SLAB == 2) {  // vertices of the next shard: accumulate in the plane buffer that is sent to it (3-float rows)
+              if (fslot[0] != 0xFFFFFFFFu) { d0 = a.fnormals + 3ull * fslot[0]; q0 = false; }
+              if (fslot[1] != 0xFFFFFFFFu) { d1 = a.fnormals + 3ull * fslot[1]; q1 = false; }
+              if (fslot[2] != 0xFFFFFFFFu) { d2 = a.fnormals + 3ull * fslot[2]; q2 = false; }
             }
             // legacy faces (t0,t2,t1) = the stored row reversed
-            if (a.transpose) face_normal_scatter(p[2], p[1], p[0], d2, d1, d0);
-            else face_normal_scatter(p[0], p[1], p[2], d0, d1, d2);
+            if (a.transpose) face_normal_scatter(p[2], p[1], p[0], d2, d1, d0, q2, q1, q0);
+            else face_normal_scatter(p[0], p[1], p[2], d0, d1, d2, q0, q1, q2);
           }
         }
         __syncwarp();
@@ -1934,10 +1948,12 @@ __global__ void __launch_bounds__(NT_V) k_import_plane_normals(const VolParams v
       if ((vidx >> 8) != 0u || s6 >= 4u) continue;
       const uint32_t ef = tf * TF + (vidx & 31u), em = tm * TM + ((vidx >> 5) & 7u);
       const float* in = src + 3ull * (4ull * ((size_t)em * vp.Efp + ef) + s6);
-      float* nn = a.normals + 3ull * ((tl[ci].a & 0xFFFFFFFFull) + __ldg(a.perm + h.gbase + i));
-      nn[0] = __fadd_rn(nn[0], in[0]);
-      nn[1] = __fadd_rn(nn[1], in[1]);
-      nn[2] = __fadd_rn(nn[2], in[2]);
+      float4* nn = a.nacc + ((tl[ci].a & 0xFFFFFFFFull) + __ldg(a.perm + h.gbase + i));
+      float4 acc = *nn;
+      acc.x = __fadd_rn(acc.x, in[0]);
+      acc.y = __fadd_rn(acc.y, in[1]);
+      acc.z = __fadd_rn(acc.z, in[2]);
+      *nn = acc;
     }
   }
 }
@@ -1969,6 +1985,19 @@ __global__ void __launch_bounds__(256) k_normals_normalize(float* normals, u64 n
     float x = normals[3 * i], y = normals[3 * i + 1], z = normals[3 * i + 2];
     float l = len3(x, y, z);
     if (l != 1.0f) { x = __fdiv_rn(x, l); y = __fdiv_rn(y, l); z = __fdiv_rn(z, l); }  // 0/0 -> NaN like hat()
+    normals[3 * i] = x; normals[3 * i + 1] = y; normals[3 * i + 2] = z;
+  }
+}
+
+// pass 2's float4 accumulation rows -> unit normals in the packed [V][3] output (hat(): 0/0 -> NaN like the reference)
+__global__ void __launch_bounds__(256) k_normals_normalize4(const float4* __restrict__ acc, float* normals, u64 nV) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (; i < nV; i += stride) {
+    const float4 v = acc[i];
+    float x = v.x, y = v.y, z = v.z;
+    const float l = len3(x, y, z);
+    if (l != 1.0f) { x = __fdiv_rn(x, l); y = __fdiv_rn(y, l); z = __fdiv_rn(z, l); }
     normals[3 * i] = x; normals[3 * i + 1] = y; normals[3 * i + 2] = z;
   }
 }
