@@ -514,6 +514,24 @@ def main():
     except Exception:
       pinned = None
     d2h = 0
+    # what the platform gives a plain pinned copy while every rank copies at once (the e2e figure is PCIe-bound:
+    # this is its ceiling; with 8 ranks the host side -- shared PCIe switches / memory -- sets it, not the GPUs)
+    h2d_plain = None
+    try:
+      nprobe = int(min(hnp.nbytes, 2 << 30))
+      src = torch.from_numpy(hnp.reshape(-1).view(np.uint8)[:nprobe])
+      dst = torch.empty(nprobe, dtype=torch.uint8, device=f"cuda:{dev}")
+      dst.copy_(src, non_blocking=True)
+      barrier()
+      t0 = time.perf_counter()
+      for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+      torch.cuda.synchronize()
+      h2d_plain = 3 * nprobe / 1e9 / (time.perf_counter() - t0)
+      del dst, src
+      torch.cuda.empty_cache()
+    except Exception:
+      pass
 
     phase = {"mesh_call_ms": 0.0, "get_loop_ms": 0.0, "h2d_ms": 0.0, "classify_ms": 0.0, "emit_ms": 0.0}
 
@@ -555,7 +573,10 @@ def main():
            "d2h_bytes_per_step": int(d2h), "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
            "host_buffer": "cudaHostRegister'ed numpy" if pinned is not None else "pageable numpy",
            "phases_ms": {k: v / args.e2e_steps for k, v in phase.items()},
-           "pcie_gbs": {"h2d": (hnp.nbytes / 1e9) / (phase["h2d_ms"] / args.e2e_steps / 1e3) if phase["h2d_ms"] > 0 else None},
+           "pcie_gbs": {"h2d": (hnp.nbytes / 1e9) / (phase["h2d_ms"] / args.e2e_steps / 1e3) if phase["h2d_ms"] > 0 else None,
+                        "h2d_plain_copy_all_ranks_at_once": h2d_plain,
+                        "note": "rank 0; h2d = the volume upload inside mesh(); plain copy = torch copy_ of 2 GiB of the same "
+                                "pinned buffer while every rank does the same (the platform's ceiling for this step)"},
            "api": "zmesh_b200.Mesher.mesh(ndarray) + get(id) for every id (rank-local slab when sharded)"}
 
   # ---- CPU baseline beside it (rank 0, N = 1): the compiled reference on one host core, two passes over a

@@ -189,6 +189,16 @@ int zm_finalize_begin(zm_handle* h, int normals, int voxel_centered, int transpo
  * (vertices 3*V_total floats, faces 3*T_total uint32, normals 3*V_total floats or NULL). */
 int zm_fetch_all(zm_handle* h, float* vertices, uint32_t* faces, float* normals_out);
 
+/* Mesh wire format on the device (replaces Mesh.to_precomputed applied label by label, zmesh/mesh.py:257-269, the step
+ * that follows Mesher.get in production callers): zm_pack_precomputed finalizes (no normals) and gathers, for every id
+ * in ascending order, the Neuroglancer "Precomputed" object -- uint32 Nv | float32 vertices [Nv][3] | uint32 faces
+ * [Nf][3] -- into one device buffer; zm_fetch_precomputed copies it to dst_host[total_bytes] (pinned memory from
+ * zm_host_alloc for full speed) in ONE transfer and returns the ids and the byte offset of every object
+ * (byte_offsets_out[n_objects] = total_bytes). */
+int zm_pack_precomputed(zm_handle* h, int voxel_centered, const float centering_offset[3], uint64_t* n_objects,
+                        uint64_t* total_bytes);
+int zm_fetch_precomputed(zm_handle* h, void* dst_host, uint64_t* labels_out, uint64_t* byte_offsets_out);
+
 /* Page-locked host memory for zm_fetch_all destinations (full-speed D2H); NULL on failure. */
 void* zm_host_alloc(uint64_t bytes);
 void zm_host_free(void* p);

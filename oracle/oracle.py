@@ -304,6 +304,15 @@ def assert_same_mesh(got, want, normals_tol: float = 1e-5, what: str = ""):
     assert ok.all(), f"{what}: normals differ by up to {np.nanmax(np.abs(gn - wn))}"
 
 
+def to_precomputed_bytes(vertices: np.ndarray, faces: np.ndarray) -> bytes:
+  """Restatement of the reference's Mesh.to_precomputed (zmesh/mesh.py:257-269): uint32 Nv, then the float32 vertices
+  in C order, then the uint32 faces in C order.  Pinned against the unmodified reference encoder by
+  tests/golden/codec_golden.npz (tools/make_codec_golden.py)."""
+  v = np.ascontiguousarray(vertices, dtype=np.float32)
+  f = np.ascontiguousarray(faces).astype(np.uint32, copy=False)
+  return b"".join((np.uint32(v.shape[0]).tobytes(), v.tobytes("C"), f.tobytes("C")))
+
+
 # ------------------------------------------------------------------------------------------------
 # deterministic synthetic volumes (SURVEY.md section 8d)
 

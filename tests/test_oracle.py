@@ -110,3 +110,28 @@ def test_fanc_bug_c_and_f_order(kind, fanc):
     p = OracleMesher((1, 1, 1), "port")
     p.mesh(np.ascontiguousarray(vol))
     assert_same_mesh(p.get(1), b, what="fanc port vs reference")
+
+
+def test_codecs_match_reference_encoders():
+  """Mesh wire formats: the drop-in's encoders and the oracle's Precomputed restatement reproduce, byte
+  for byte, what the UNMODIFIED reference encoders wrote into tests/golden/codec_golden.npz (tools/make_codec_golden.py:
+  zmesh/mesh.py:257-269 to_precomputed, :348-376 to_ply, :321-346 to_obj), and decode them back."""
+  import os
+  from oracle.oracle import to_precomputed_bytes
+  from tests.conftest import GOLDEN
+  from zmesh_b200.mesh import Mesh
+  g = np.load(os.path.join(GOLDEN, "codec_golden.npz"))
+  names = sorted({k.split("/")[0] for k in g.files})
+  assert names == ["empty", "halfvoxel", "mid", "tiny"]
+  for name in names:
+    v, f = g[f"{name}/v"], g[f"{name}/f"]
+    m = Mesh(v, f, None)
+    want = {k: g[f"{name}/{k}"].tobytes() for k in ("precomputed", "ply", "obj")}
+    assert m.to_precomputed() == want["precomputed"] == to_precomputed_bytes(v, f), name
+    assert bytes(m.to_ply()) == want["ply"], name
+    assert m.to_obj() == want["obj"], name
+    back = Mesh.from_precomputed(want["precomputed"])
+    assert np.array_equal(back.vertices, v) and np.array_equal(back.faces, f)
+    if len(v):
+      back = Mesh.from_ply(want["ply"])
+      assert np.array_equal(back.vertices, v) and np.array_equal(back.faces, f)

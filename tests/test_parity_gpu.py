@@ -488,3 +488,26 @@ def test_config4_slab_against_reference(Mesher):
   for lbl in ids[::4]:
     assert_same_mesh(m.get(lbl, normals=True, voxel_centered=True), cpu.get(lbl, normals=True, voxel_centered=True),
                      NORMALS_TOL, what=f"c4 slab label {lbl}")
+
+
+def test_precomputed_objects_from_the_device(Mesher, connectomics):
+  """Mesher.precomputed() -- objects laid out by a device kernel, one transfer -- returns, for every id,
+  exactly the bytes the reference's encoder (zmesh/mesh.py:257-269; oracle.to_precomputed_bytes is pinned to it by
+  tests/golden/codec_golden.npz) produces for get(id), and they decode to the oracle's mesh."""
+  from oracle.oracle import to_precomputed_bytes
+  from zmesh_b200 import Mesh
+  vol = np.asfortranarray(connectomics[200:328, 200:328, 200:264])
+  for vc in (False, True):
+    m = Mesher((4, 4, 40))
+    m.mesh(vol, close=True)
+    objs = m.precomputed(voxel_centered=vc)
+    ids = m.ids()
+    assert sorted(objs) == ids and len(ids) > 20
+    cpu = OracleMesher((4, 4, 40), "port")
+    cpu.mesh(vol, close=True)
+    for lbl in ids:
+      g = m.get(lbl, voxel_centered=vc)
+      assert bytes(objs[lbl]) == to_precomputed_bytes(g.vertices, g.faces), lbl
+    for lbl in ids[::7]:
+      assert_same_mesh(Mesh.from_precomputed(bytes(objs[lbl])), cpu.get(lbl, voxel_centered=vc), what=f"precomputed {lbl}")
+    assert m.erase(ids[0]) and ids[0] not in m.precomputed(voxel_centered=vc)

@@ -95,6 +95,8 @@ SYMBOLS = {
   "zm_host_alloc": (C.c_void_p, [C.c_uint64]),
   "zm_host_free": (None, [C.c_void_p]),
   "zm_stats": (C.c_int, [C.c_void_p, C.POINTER(zm_stats_t)]),
+  "zm_pack_precomputed": (C.c_int, [C.c_void_p, C.c_int, _f3, _u64p, _u64p]),
+  "zm_fetch_precomputed": (C.c_int, [C.c_void_p, C.c_void_p, _u64p, _u64p]),
   "zm_nccl_unique_id": (C.c_int, [C.c_void_p]),
   "zm_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
   "zm_comm_destroy": (C.c_int, [C.c_void_p]),

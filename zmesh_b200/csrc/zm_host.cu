@@ -76,6 +76,8 @@ struct zm_handle {
   DevBuf d_rowinfo, d_perm, d_vinfo, d_rec, d_tl, d_hdr, d_dense;
   // results (device)
   DevBuf d_faces, d_verts, d_normals;
+  DevBuf d_pack, d_packtab;  // Precomputed objects of all labels (zm_pack_precomputed) and their offset table
+  std::vector<uint64_t> pack_labels, pack_off;  // ids in ascending order; byte offset of every object (+ the end)
   DevBuf d_nacc;  // float4 accumulation rows of the normals (pass 2 adds one vector atomic per triangle corner)
   DevBuf d_voff, d_tmpA, d_tmpB;     // slab sharding: per-table-slot index offsets; upload scratch
   bool tl_fixed = false, have_voff = false, slab_mode = false;
@@ -263,6 +265,8 @@ void drop_results(zm_handle* h) {
   h->sorted_ids.clear();
   h->dir_pending = false;
   h->nlabels = 0;
+  h->pack_labels.clear();
+  h->pack_off.clear();
   h->bulk_labels.clear();
   h->bulk_voff.clear();
   h->bulk_foff.clear();
@@ -755,7 +759,7 @@ void zm_destroy(zm_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->d_vol, &h->d_keys, &h->d_cnt, &h->d_offV, &h->d_offT, &h->d_list, &h->d_partial, &h->d_ctl,
                     &h->d_rowinfo, &h->d_perm, &h->d_vinfo, &h->d_rec, &h->d_tl, &h->d_hdr,
-                    &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals, &h->d_nacc, &h->d_voff, &h->d_tmpA, &h->d_tmpB})
+                    &h->d_dense, &h->d_faces, &h->d_verts, &h->d_normals, &h->d_nacc, &h->d_pack, &h->d_packtab, &h->d_voff, &h->d_tmpA, &h->d_tmpB})
     b->release();
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
   if (h->h_list) cudaFreeHost(h->h_list);
@@ -1091,6 +1095,68 @@ int zm_fetch_all(zm_handle* h, float* vertices, uint32_t* faces, float* normals_
   ZM_CUDA(h, cudaStreamSynchronize(st));
   if (h->fin.transpose && faces)
     for (uint64_t i = 0; i < h->Ttot; ++i) std::swap(faces[3 * i], faces[3 * i + 2]);
+  return ZM_OK;
+}
+
+int zm_pack_precomputed(zm_handle* h, int voxel_centered, const float centering_offset[3], uint64_t* n_objects,
+                        uint64_t* total_bytes) {
+  if (!h || !n_objects || !total_bytes) return ZM_ERR_INVALID;
+  *n_objects = *total_bytes = 0;
+  int rc = do_finalize(h, 0, voxel_centered, 0, centering_offset);
+  if (rc != ZM_OK) return rc;
+  rc = ensure_directory(h);
+  if (rc != ZM_OK) return rc;
+  h->pack_labels.clear();
+  h->pack_off.clear();
+  const size_t nl = h->sorted_ids.size();
+  if (nl == 0) return ZM_OK;
+  // table: word[nl + 1], voff[nl], nv[nl], foff[nl]  (ids in ascending order; erased labels are not in sorted_ids)
+  std::vector<uint64_t> tab(4 * nl + 1);
+  uint64_t w = 0;
+  for (size_t i = 0; i < nl; ++i) {
+    const LabelRec& r = h->recs[h->index[h->sorted_ids[i]]];
+    tab[i] = w;
+    tab[nl + 1 + i] = r.voff;
+    tab[2 * nl + 1 + i] = r.nv;
+    tab[3 * nl + 1 + i] = r.foff;
+    h->pack_labels.push_back(r.label);
+    h->pack_off.push_back(4 * w);
+    w += 1 + 3 * r.nv + 3 * r.nt;
+  }
+  tab[nl] = w;
+  h->pack_off.push_back(4 * w);
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  ZM_CUDA(h, h->d_packtab.ensure(tab.size() * 8));
+  ZM_CUDA(h, h->d_pack.ensure((size_t)w * 4));
+  cudaStream_t st = h->stream;
+  ZM_CUDA(h, cudaMemcpyAsync(h->d_packtab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, st));
+  PackArgs a{};
+  const u64* t = h->d_packtab.as<u64>();
+  a.word = t; a.voff = t + nl + 1; a.nv = t + 2 * nl + 1; a.foff = t + 3 * nl + 1;
+  a.verts = h->d_verts.as<uint32_t>();
+  a.faces = h->d_faces.as<uint32_t>();
+  a.out = h->d_pack.as<uint32_t>();
+  a.total = w;
+  a.nl = (uint32_t)nl;
+  const uint64_t nchunks = (w + PACK_CHUNK - 1) / PACK_CHUNK;
+  k_pack_precomputed<<<(uint32_t)std::min<uint64_t>(nchunks, (uint64_t)h->num_sms * 16), 256, 0, st>>>(a);
+  ZM_CUDA(h, cudaGetLastError());
+  ZM_CUDA(h, cudaStreamSynchronize(st));  // (the table is a host vector)
+  *n_objects = nl;
+  *total_bytes = 4 * w;
+  return ZM_OK;
+}
+
+int zm_fetch_precomputed(zm_handle* h, void* dst_host, uint64_t* labels_out, uint64_t* byte_offsets_out) {
+  if (!h) return ZM_ERR_INVALID;
+  const size_t nl = h->pack_labels.size();
+  if (nl == 0) return ZM_OK;
+  if (!dst_host || !labels_out || !byte_offsets_out) return fail(h, ZM_ERR_INVALID, "null output buffer");
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  ZM_CUDA(h, cudaMemcpyAsync(dst_host, h->d_pack.p, (size_t)h->pack_off[nl], cudaMemcpyDeviceToHost, h->stream));
+  memcpy(labels_out, h->pack_labels.data(), nl * 8);
+  memcpy(byte_offsets_out, h->pack_off.data(), (nl + 1) * 8);
+  ZM_CUDA(h, cudaStreamSynchronize(h->stream));
   return ZM_OK;
 }
 

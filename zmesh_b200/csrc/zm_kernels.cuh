@@ -2003,6 +2003,54 @@ __global__ void __launch_bounds__(256) k_normals_normalize4(const float4* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Mesh wire format on the device: the Neuroglancer "Precomputed" layout of every label --
+// uint32 Nv | float32 vertices [Nv][3] | uint32 faces [Nf][3] (zmesh/mesh.py:257-269) -- gathered from pass 2's final
+// arrays into ONE buffer in label order, so that a single device-to-host transfer lands ready-to-write objects.
+// word[i] .. word[i + 1] = the 4-byte words of label i's object.  A CTA copies chunks of PACK_CHUNK words; the label
+// of a chunk's first word is found by binary search, later ones by walking the (monotone) table.
+constexpr int PACK_CHUNK = 4096;
+struct PackArgs {
+  const u64* word;   // [nl + 1] first output word of every label
+  const u64* voff;   // [nl] first vertex row,  nv[nl] vertex count
+  const u64* nv;
+  const u64* foff;   // [nl] first face row
+  const uint32_t* verts;  // float32 bit patterns [V][3]
+  const uint32_t* faces;  // [T][3]
+  uint32_t* out;
+  u64 total;         // word[nl]
+  uint32_t nl;
+};
+__global__ void __launch_bounds__(256) k_pack_precomputed(const PackArgs a) {
+  __shared__ uint32_t s_first;
+  const u64 nchunks = (a.total + PACK_CHUNK - 1) / PACK_CHUNK;
+  for (u64 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const u64 w0 = c * PACK_CHUNK;
+    if (threadIdx.x == 0) {
+      uint32_t lo = 0, hi = a.nl - 1;  // largest i with word[i] <= w0
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (a.word[mid] <= w0) lo = mid; else hi = mid - 1;
+      }
+      s_first = lo;
+    }
+    __syncthreads();
+    uint32_t i = s_first;
+    const u64 w1 = w0 + PACK_CHUNK < a.total ? w0 + PACK_CHUNK : a.total;
+    for (u64 w = w0 + threadIdx.x; w < w1; w += blockDim.x) {
+      while (w >= a.word[i + 1]) ++i;
+      const u64 r = w - a.word[i];
+      const u64 nv = a.nv[i];
+      uint32_t val;
+      if (r == 0) val = (uint32_t)nv;
+      else if (r - 1 < 3 * nv) val = a.verts[3 * a.voff[i] + (r - 1)];
+      else val = a.faces[3 * a.foff[i] + (r - 1 - 3 * nv)];
+      a.out[w] = val;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // synthetic jittered-grid Voronoi volume (benchmark/test input)
 
 __host__ __device__ __forceinline__ u64 splitmix64(u64 x) {

@@ -485,6 +485,26 @@ class Mesher:
       "vertices_dev": view.vertices_dev, "faces_dev": view.faces_dev, "normals_dev": view.normals_dev,
     }
 
+  def precomputed(self, voxel_centered=False) -> dict:
+    """{id: bytes-like} -- the Neuroglancer Precomputed object of every id (what Mesh.to_precomputed() returns for
+    get(id), zmesh/mesh.py:257-269), laid out on the device and moved to the host in ONE transfer; the values are
+    memoryviews of a pinned block (bytes(v) makes an owned copy)."""
+    off = _f3(self._voxel_res)
+    n, total = C.c_uint64(0), C.c_uint64(0)
+    self._check(self._lib.zm_pack_precomputed(self._h, int(bool(voxel_centered)), off.ctypes.data_as(C.POINTER(C.c_float)),
+                                              C.byref(n), C.byref(total)))
+    if n.value == 0:
+      return {}
+    blk = self._pinned(int(total.value))
+    buf = blk.view(np.uint8, (int(total.value),), 0)
+    labels = np.empty(n.value, dtype=np.uint64)
+    offs = np.empty(n.value + 1, dtype=np.uint64)
+    self._check(self._lib.zm_fetch_precomputed(self._h, C.c_void_p(buf.ctypes.data), labels.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                               offs.ctypes.data_as(C.POINTER(C.c_uint64))))
+    mv = memoryview(buf)
+    o = offs.tolist()
+    return {int(l): mv[o[i]:o[i + 1]] for i, l in enumerate(labels.tolist())}
+
   def finalize_begin(self, normals=False, voxel_centered=False, transpose=False):
     """Slab shards: start pass 2 for all tiles but the top layer (see zm_finalize_begin); follow with finalize()."""
     off = _f3(self._voxel_res)
