@@ -249,6 +249,10 @@ int zm_slab_range(uint64_t full_extent, int close, int rank, int world, zm_slab*
 int zm_slab_step(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz, int c_order,
                  int close, int mem_kind, uint64_t full_extent, uint64_t buf_lo, int finalize, int normals,
                  int voxel_centered, const float centering_offset[3]);
+/* Pass 2 of a slab step that was run with finalize = 0, or a later request for normals / another vertex transform:
+ * zm_finalize for a shard, including the normals plane exchange.  COLLECTIVE when normals are (re)computed: every shard
+ * of the step must call it with the same arguments. */
+int zm_slab_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, const float centering_offset[3]);
 
 /* Blocks until all work queued by this handle has finished. */
 int zm_sync(zm_handle* h);

@@ -24,8 +24,9 @@ def main():
 
   shape, pitch = (256, 256, 320), 40
   ok = True
-  for close in (False, True):
-    sm = ShardedMesher((4, 4, 40), device=local)
+  # (close, native): the native NCCL step of the C++ layer, and the same step driven from Python over torch.distributed
+  for close, native in ((False, True), (True, True), (False, False), (True, False)):
+    sm = ShardedMesher((4, 4, 40), device=local, native=native)
     cube_lo, cube_hi, in_lo, in_hi, last = sm.planes(shape[2], close)
     slab = voronoi_device((shape[0], shape[1], in_hi - in_lo), pitch, np.uint64, seed=5, order="F",
                           origin=(0, 0, in_lo), full_shape=shape, device=local)
@@ -53,7 +54,7 @@ def main():
             print(e, flush=True)
             bad += 1
     if rank == 0:
-      print(f"close={close}: {len(ids)} labels over {world} ranks, {bad} mismatches", flush=True)
+      print(f"close={close} native={native}: {len(ids)} labels over {world} ranks, {bad} mismatches", flush=True)
       ok = ok and bad == 0 and len(ids) > 0
   flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
   dist.broadcast(flag, 0)

@@ -145,3 +145,42 @@ def test_multi_process_nccl(build_all):
                       "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "multi_gpu_check.py")],
                      capture_output=True, text=True, timeout=900)
   assert r.returncode == 0 and "MULTI_GPU_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+MULTI_CASES = [
+  ("voronoi_u64_F_close", lambda: voronoi_volume((72, 64, 96), 20, np.uint64, 3, "F"), (4, 4, 40), True),
+  ("random_u32_C", lambda: random_volume((40, 20, 33), 40, np.uint32, 7, "C"), (1, 2, 3), False),
+  ("boundary_kat_close", _kat_volume, (4, 4, 40), True),
+  ("thin_one_device", lambda: random_volume((9, 9, 2), 4, np.uint8, 1, "F"), (1, 1, 1), False),
+]
+
+
+@pytest.mark.parametrize("case", MULTI_CASES, ids=[c[0] for c in MULTI_CASES])
+def test_multi_device_mesher_in_one_process(build_all, case):
+  """`Mesher(voxel_res, devices=[...])` (multi-GPU behind the drop-in API, one process, native NCCL
+  step): every label -- vertices, faces, normals, the legacy accessor, erase -- equals the oracle's.  Needs >= 2 GPUs."""
+  import torch
+  from zmesh_b200 import Mesher, MultiDeviceMesher
+  ndev = torch.cuda.device_count()
+  if ndev < 2:
+    pytest.skip("needs at least 2 GPUs")
+  name, make, res, close = case
+  vol = make()
+  cpu = OracleMesher(res, "port")
+  cpu.mesh(vol, close=close)
+  for devices in ([0, 1], list(range(min(ndev, 4)))):
+    m = Mesher(res, devices=devices)
+    assert isinstance(m, MultiDeviceMesher)
+    m.mesh(vol, close=close)
+    ids = m.ids()
+    assert ids == sorted(cpu.ids()), (name, devices)
+    for lbl in ids:
+      assert_same_mesh(m.get(lbl, voxel_centered=True), cpu.get(lbl, voxel_centered=True), what=f"{name} {devices} {lbl}")
+    for lbl in ids[::3]:
+      assert_same_mesh(m.get(lbl, normals=True), cpu.get(lbl, normals=True), 1e-5, what=f"{name} {devices} {lbl} normals")
+      assert_same_mesh(m.get_mesh(lbl), cpu.get_mesh(lbl), what=f"{name} {devices} {lbl} legacy")
+    if ids:
+      assert m.erase(ids[0]) is True and m.erase(ids[0]) is False and m.ids() == ids[1:]
+      assert m.get(ids[0]).empty()
+    m.clear()
+    assert m.ids() == []

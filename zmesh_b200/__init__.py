@@ -11,6 +11,7 @@ is no CPU fallback.
 """
 from .mesh import Mesh
 from .mesher import Mesher
+from .multi import MultiDeviceMesher
 
-__all__ = ["Mesh", "Mesher"]
+__all__ = ["Mesh", "Mesher", "MultiDeviceMesher"]
 __version__ = "0.1.0"

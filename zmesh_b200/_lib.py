@@ -103,6 +103,7 @@ SYMBOLS = {
   "zm_slab_range": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(zm_slab), _u64p, _u64p]),
   "zm_slab_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int,
                              C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, _f3]),
+  "zm_slab_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _f3]),
   "zm_sync": (C.c_int, [C.c_void_p]),
   "zm_last_error": (C.c_char_p, [C.c_void_p]),
   "zm_version": (C.c_char_p, []),

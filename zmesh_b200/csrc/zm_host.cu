@@ -1279,6 +1279,45 @@ int zm_slab_range(uint64_t full_extent, int close, int rank, int world, zm_slab*
   return ZM_OK;
 }
 
+int zm_slab_finalize(zm_handle* h, int normals, int voxel_centered, int transpose, const float centering_offset[3]) {
+  if (!h) return ZM_ERR_INVALID;
+  if (!h->comm) return fail(h, ZM_ERR_STATE, "zm_comm_init has not been called");
+  if (!h->slab_mode) return fail(h, ZM_ERR_STATE, "zm_slab_step has not been called");
+  const NcclApi& N = nccl_api();
+  const bool last = h->rank == h->world - 1;
+  const bool want_normals = normals && !(h->fin.normals_valid && h->fin.normals_transpose == (transpose ? 1 : 0));
+  const uint64_t n = zm_plane_elems(h);
+  cudaStream_t st = h->stream;
+  int rc;
+  ZM_CUDA(h, cudaSetDevice(h->device));
+  if (want_normals && !last) {
+    ZM_CUDA(h, h->d_nplane_out.ensure(n * 12));
+    h->nplane_out = h->d_nplane_out.as<float>();
+  }
+  if (!last) {  // all tiles below the top layer with the cheaper kernel variant (they never look at the boundary plane)
+    rc = do_finalize(h, normals, voxel_centered, transpose, centering_offset, true);
+    if (rc != ZM_OK) return rc;
+  }
+  rc = do_finalize(h, normals, voxel_centered, transpose, centering_offset);
+  if (rc != ZM_OK) return rc;
+  if (want_normals) {
+    // normal contributions of the top cube layer to the next shard's first-plane vertices: rank r -> r + 1 (collective:
+    // every shard of the step must make this call)
+    if (h->rank > 0) ZM_CUDA(h, h->d_nplane_in.ensure(n * 12));
+    ZM_NCCL(h, N.GroupStart());
+    if (!last) ZM_NCCL(h, N.Send(h->d_nplane_out.p, n * 3, ncclFloat32, h->rank + 1, h->comm_p2p, st));
+    if (h->rank > 0) ZM_NCCL(h, N.Recv(h->d_nplane_in.p, n * 3, ncclFloat32, h->rank - 1, h->comm_p2p, st));
+    ZM_NCCL(h, N.GroupEnd());
+    if (h->rank > 0 && h->Vtot && h->n_work) {
+      rc = zm_add_normal_plane(h, h->d_nplane_in.as<float>());
+      if (rc != ZM_OK) return rc;
+    }
+    rc = zm_finish_normals(h);
+    if (rc != ZM_OK) return rc;
+  }
+  return ZM_OK;
+}
+
 int zm_slab_step(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz, int c_order,
                  int close, int mem_kind, uint64_t full_extent, uint64_t buf_lo, int finalize, int normals,
                  int voxel_centered, const float centering_offset[3]) {
@@ -1321,44 +1360,19 @@ int zm_slab_step(zm_handle* h, const void* labels, int label_bytes, uint64_t sx,
     ZM_NCCL(h, N.GroupEnd());
     h->foreign = last ? nullptr : h->d_plane_recv.as<uint32_t>();
     ZM_CUDA(h, cudaEventRecord(h->ev_comm[1], st));
-    const bool pass2 = finalize || normals;
-    if (pass2 && !last) {
-      if (normals) {
-        ZM_CUDA(h, h->d_nplane_out.ensure(n * 12));
-        h->nplane_out = h->d_nplane_out.as<float>();
-      }
-      // all tiles below the top layer with the cheaper kernel variant (they never look at the boundary plane)
-      rc = do_finalize(h, normals, voxel_centered, 0, centering_offset, true);
-      if (rc != ZM_OK) return rc;
-    }
-    if (!pass2) {  // (the caller finalizes later: only the overflow check is left, it needs the host)
+    if (!(finalize || normals)) {  // (the caller finalizes later: only the overflow check is left, it needs the host)
       ZM_CUDA(h, cudaMemcpyAsync(&h->h_ctl->flags, &h->d_ctl.as<Control>()->flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
       ZM_CUDA(h, cudaStreamSynchronize(st));
       if (h->h_ctl->flags & FLAG_DIR) { h->dir_cap *= 4; continue; }
       return ZM_OK;
     }
-    rc = do_finalize(h, normals, voxel_centered, 0, centering_offset);
+    rc = zm_slab_finalize(h, normals, voxel_centered, 0, centering_offset);
     if (rc == ZM_ERR_STATE && (h->h_ctl->flags & FLAG_DIR)) {  // every shard sees every directory size: all of them repeat
       h->dir_cap *= 4;
       continue;
     }
-    if (rc != ZM_OK) return rc;
-    cudaEventElapsedTime(&h->stats.ms_exchange, h->ev_comm[0], h->ev_comm[1]);  // (waits for the slowest rank included)
-    if (normals) {
-      // 3. normal contributions of the top cube layer to the next shard's first-plane vertices: rank r -> r + 1
-      if (h->rank > 0) ZM_CUDA(h, h->d_nplane_in.ensure(n * 12));
-      ZM_NCCL(h, N.GroupStart());
-      if (!last) ZM_NCCL(h, N.Send(h->d_nplane_out.p, n * 3, ncclFloat32, h->rank + 1, h->comm_p2p, st));
-      if (h->rank > 0) ZM_NCCL(h, N.Recv(h->d_nplane_in.p, n * 3, ncclFloat32, h->rank - 1, h->comm_p2p, st));
-      ZM_NCCL(h, N.GroupEnd());
-      if (h->rank > 0) {
-        rc = zm_add_normal_plane(h, h->d_nplane_in.as<float>());
-        if (rc != ZM_OK) return rc;
-      }
-      rc = zm_finish_normals(h);
-      if (rc != ZM_OK) return rc;
-    }
-    return ZM_OK;
+    if (rc == ZM_OK) cudaEventElapsedTime(&h->stats.ms_exchange, h->ev_comm[0], h->ev_comm[1]);  // (waits for the slowest rank included)
+    return rc;
   }
   return fail(h, ZM_ERR_UNSUPPORTED, "slab step: the label directory exchange did not converge");
 }

@@ -97,7 +97,16 @@ class _Stage:
 class Mesher:
   """Represents a meshed volume: call mesher.mesh(labels), then mesher.get(label)."""
 
-  def __init__(self, voxel_res, device: int = -1):
+  def __new__(cls, voxel_res=None, device: int = -1, devices=None):
+    # Mesher(voxel_res, devices=[0, 1, ...]): the same API over several GPUs of the node (zmesh_b200/multi.py)
+    if cls is Mesher and devices is not None and len(devices) > 1:
+      from .multi import MultiDeviceMesher
+      return MultiDeviceMesher(voxel_res, devices)
+    return super().__new__(cls)
+
+  def __init__(self, voxel_res, device: int = -1, devices=None):
+    if devices is not None and len(devices) == 1:
+      device = devices[0]
     self._lib = _lib.load()
     self.voxel_res = voxel_res
     self._device = int(device)
