@@ -235,15 +235,17 @@ int zm_synth_voronoi(void* dst_device, int label_bytes, const uint64_t shape[3],
  * of every tile below the top layer -> pass 2 of the top layer (-> the normals plane exchange).  The host issues a
  * dozen launches after the one synchronisation zm_mesh_slab needs; the Python/torch.distributed path costs ~2 ms of
  * exposed host time per step at 8 GPUs.
- *   zm_nccl_unique_id   128-byte ncclUniqueId (call on one rank, broadcast the bytes by any means; two are needed)
- *   zm_comm_init        ncclCommInitRank for this handle's device: one communicator for the collectives, one for the
- *                       neighbour transfers
+ *   zm_nccl_unique_id   128-byte ncclUniqueId (call on one rank, broadcast the bytes by any means; `world` are needed)
+ *   zm_comm_init        ncclCommInitRank for this handle's device: one communicator of all shards for the directory
+ *                       all-gather (id_collectives) and one 2-rank communicator per neighbour pair for the boundary
+ *                       planes (id_pairs: world - 1 ids of 128 bytes, id k = shards k and k + 1; a send/recv inside a
+ *                       2-rank communicator gets all NVLink channels)
  *   zm_slab_range       the cube planes [cube_lo, cube_hi) of `rank` and the input planes [in_lo, in_hi) it must supply
  *   zm_slab_step        `labels` holds input planes [buf_lo, buf_lo + extent along the slab axis) covering that range;
  *                       finalize / normals / voxel_centered as zm_finalize (results stay distributed: zm_get returns
  *                       this shard's part of a label, face indices are cross-shard) */
 int zm_nccl_unique_id(void* out128);
-int zm_comm_init(zm_handle* h, const void* id_collectives, const void* id_neighbours, int world, int rank);
+int zm_comm_init(zm_handle* h, const void* id_collectives, const void* id_pairs, int world, int rank);
 int zm_comm_destroy(zm_handle* h);
 int zm_slab_range(uint64_t full_extent, int close, int rank, int world, zm_slab* slab, uint64_t* in_lo, uint64_t* in_hi);
 int zm_slab_step(zm_handle* h, const void* labels, int label_bytes, uint64_t sx, uint64_t sy, uint64_t sz, int c_order,

@@ -225,8 +225,11 @@ class Mesher:
       raise RuntimeError(f"zmesh_b200: {msg.decode() if msg else rc}")
     return buf.raw
 
-  def comm_init(self, id_collectives: bytes, id_neighbours: bytes, world: int, rank: int):
-    self._check(self._lib.zm_comm_init(self._h, id_collectives, id_neighbours, int(world), int(rank)))
+  def comm_init(self, id_collectives: bytes, id_pairs: bytes, world: int, rank: int):
+    """id_pairs: (world - 1) * 128 bytes, id k names the 2-rank communicator of shards k and k + 1."""
+    if len(id_pairs) != 128 * max(int(world) - 1, 0):
+      raise ValueError("id_pairs must hold world - 1 ids of 128 bytes")
+    self._check(self._lib.zm_comm_init(self._h, id_collectives, id_pairs if id_pairs else None, int(world), int(rank)))
 
   def slab_step(self, data, full_extent: int, buf_lo: int, close=False, finalize=True, normals=False, voxel_centered=False):
     """One whole slab step on this rank (see zm_slab_step): `data` holds the input planes [buf_lo, buf_lo + n) along the

@@ -32,8 +32,8 @@ class MultiDeviceMesher:
     self._close = False
     self._normals_key = None
     self.voxel_res = voxel_res
-    ids = (Mesher.nccl_unique_id(), Mesher.nccl_unique_id())
     world = len(self._parts)
+    ids = (Mesher.nccl_unique_id(), b"".join(Mesher.nccl_unique_id() for _ in range(world - 1)))
     self._each(lambda r, p: p.comm_init(ids[0], ids[1], world, r))
 
   def _each(self, fn, parts=None):

@@ -131,7 +131,8 @@ class ShardedMesher:
     self.mesher = Mesher(voxel_res, device=self.device)
     self.native = False
     if native and dist.get_backend(group) == "nccl":
-      ids = [Mesher.nccl_unique_id(), Mesher.nccl_unique_id()] if self.rank == 0 else [None, None]
+      ids = ([Mesher.nccl_unique_id(), b"".join(Mesher.nccl_unique_id() for _ in range(self.world - 1))]
+             if self.rank == 0 else [None, None])
       dist.broadcast_object_list(ids, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
       self.mesher.comm_init(ids[0], ids[1], self.world, self.rank)
       self.native = True
