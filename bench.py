@@ -68,6 +68,21 @@ def describe(name, wl, n_gpus=1):
                        "results stay distributed")}
 
 
+class stdout_to_stderr:
+  """NCCL prints its version banner to stdout when a communicator is created (NCCL_DEBUG=VERSION on some boxes): keep
+  stdout for the one JSON line."""
+
+  def __enter__(self):
+    sys.stdout.flush()
+    self.saved = os.dup(1)
+    os.dup2(2, 1)
+
+  def __exit__(self, *a):
+    sys.stdout.flush()
+    os.dup2(self.saved, 1)
+    os.close(self.saved)
+
+
 def load_peaks():
   p = os.path.join(ROOT, "MEASURED_PEAKS.json")
   if os.path.exists(p):
@@ -370,19 +385,10 @@ def main():
     G.build()
   if world > 1:
     torch.cuda.set_device(local_rank)
-    # NCCL prints its version banner to stdout when the communicator is created (NCCL_DEBUG=VERSION on
-    # some boxes): keep stdout for the one JSON line
-    sys.stdout.flush()
-    saved_stdout = os.dup(1)
-    os.dup2(2, 1)
-    try:
+    with stdout_to_stderr():
       dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
       dist.barrier()
       torch.cuda.synchronize()
-    finally:
-      sys.stdout.flush()
-      os.dup2(saved_stdout, 1)
-      os.close(saved_stdout)
   from zmesh_b200 import Mesher
 
   dev = local_rank
@@ -396,7 +402,9 @@ def main():
     if wl["order"] != "F":
       raise SystemExit("multi-GPU bench: Fortran-order workloads only (c1, c4, c5, c5s)")
     from zmesh_b200.sharded import ShardedMesher
-    sm = ShardedMesher(wl["res"], device=dev)
+    with stdout_to_stderr():  # (the native step creates its own NCCL communicators)
+      sm = ShardedMesher(wl["res"], device=dev)
+      torch.cuda.synchronize()
     _, _, in_lo, in_hi, _ = sm.planes(shape[2], wl["close"])
     zr = (in_lo, in_hi)
     mesher = sm.mesher
@@ -610,7 +618,8 @@ def main():
   nccl_parity = None
   if world > 1 and not args.no_parity:
     torch.cuda.set_stream(torch.cuda.default_stream(dev))
-    nccl_parity = nccl_parity_check(rank, world, local_rank)
+    with stdout_to_stderr():
+      nccl_parity = nccl_parity_check(rank, world, local_rank)
 
   if rank == 0:
     line = {

@@ -179,10 +179,12 @@ typedef struct {
 int zm_finalize(zm_handle* h, int normals, int voxel_centered, int transpose,
                 const float centering_offset[3], zm_bulk_view* view);
 
-/* Slab shards that are not the last one: start pass 2 for every tile except the top tile layer -- the only tiles
- * whose cubes reference the next shard's boundary plane -- without waiting for that plane and without synchronising
- * (the NCCL transfer of the plane overlaps these tiles).  The zm_finalize that follows, with the same arguments and
- * after zm_set_foreign_plane, emits the top layer.  A no-op for unsharded volumes and for the last shard. */
+/* Slab shards that are not the last one: run pass 2 for every tile except the top tile layer -- the only tiles whose
+ * cubes reference the next shard's boundary plane -- with the kernel variant that has no boundary-plane lookups, without
+ * synchronising.  The zm_finalize that follows, with the same arguments and after zm_set_foreign_plane, emits the top
+ * layer.  A no-op for unsharded volumes and for the last shard.  (The plane transfer itself is best queued BEFORE this
+ * call on the same stream: pass 2 is a persistent kernel that fills every SM, a transfer queued beside it on a second
+ * stream does not start until it retires -- measured) */
 int zm_finalize_begin(zm_handle* h, int normals, int voxel_centered, int transpose, const float centering_offset[3]);
 
 /* Copies the finalized arrays of all labels to host buffers in one transfer each
