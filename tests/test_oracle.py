@@ -135,3 +135,31 @@ def test_codecs_match_reference_encoders():
     if len(v):
       back = Mesh.from_ply(want["ply"])
       assert np.array_equal(back.vertices, v) and np.array_equal(back.faces, f)
+
+
+def test_c_generator_matches_numpy_generator():
+  """oracle.voronoi_volume_c (the threaded C restatement bench.py's CPU arms build their samples with) is bit-identical
+  to the numpy definition of SURVEY.md 8d for both label widths, both memory orders and sub-blocks of a larger volume."""
+  from oracle.oracle import voronoi_volume, voronoi_volume_c
+  for dt, order in ((np.uint64, "F"), (np.uint32, "C"), (np.uint16, "F"), (np.uint8, "C")):
+    a = voronoi_volume((37, 29, 23), 9, dt, 3, order, origin=(5, 11, 2), full_shape=(80, 60, 40))
+    b = voronoi_volume_c((37, 29, 23), 9, dt, 3, order, origin=(5, 11, 2), full_shape=(80, 60, 40), threads=3)
+    assert a.dtype == b.dtype and a.flags.f_contiguous == b.flags.f_contiguous and np.array_equal(a, b), (dt, order)
+
+
+def test_multiset_digest_is_order_independent_and_winding_sensitive():
+  """The O(n) fingerprint bench.py compares large samples with: invariant under vertex permutation and rotation of a
+  face's corners, changed by a flipped winding, a moved vertex or a missing face."""
+  from oracle.oracle import multiset_digest
+  vol = voronoi_volume((24, 20, 22), 8, np.uint64, 1, "F")
+  m = OracleMesher((4, 4, 40), "port")
+  m.mesh(vol)
+  g = m.get(m.ids()[0])
+  v, f = g.vertices, g.faces.astype(np.int64)
+  d = multiset_digest(v, f)
+  perm = np.random.default_rng(0).permutation(len(v))
+  inv = np.argsort(perm)
+  assert multiset_digest(v[perm], inv[f][:, [1, 2, 0]]) == d
+  assert multiset_digest(v[perm], inv[f][:, [0, 2, 1]]) != d
+  v2 = v.copy(); v2[0, 0] += 0.5
+  assert multiset_digest(v2, f) != d and multiset_digest(v, f[1:]) != d

@@ -511,3 +511,25 @@ def test_precomputed_objects_from_the_device(Mesher, connectomics):
     for lbl in ids[::7]:
       assert_same_mesh(Mesh.from_precomputed(bytes(objs[lbl])), cpu.get(lbl, voxel_centered=vc), what=f"precomputed {lbl}")
     assert m.erase(ids[0]) and ids[0] not in m.precomputed(voxel_centered=vc)
+
+
+def test_results_are_owned_by_the_caller_and_empty_before_mesh(Mesher):
+  """Round-1 advice: (1) an in-place edit of a result (mesh.vertices += offset) must not leak into a later get() of the
+  same label -- the first result is a view of the staged block, a repeated request is read back from the device;
+  (2) a mesher that has not meshed anything answers like an empty one (the reference's __init__ builds an empty
+  Mesher6464, zmesh/_zmesh.pyx:442-444)."""
+  fresh = Mesher((1, 1, 1))
+  assert fresh.ids() == [] and fresh.get(5).empty() and fresh.get(5).id == 5 and fresh.erase(5) is False
+  vol = np.zeros((12, 12, 12), dtype=np.uint32)
+  vol[2:9, 3:8, 4:10] = 5
+  m = Mesher((2, 3, 4))
+  m.mesh(vol)
+  a = m.get(5, normals=True)
+  pristine = a.vertices.copy()
+  a.vertices += 100.0
+  a.faces[:] = 0
+  b = m.get(5, normals=True)
+  assert np.array_equal(b.vertices, pristine) and b.faces.max() == len(pristine) - 1
+  assert not np.shares_memory(a.vertices, b.vertices)
+  c = m.get(5, normals=True)
+  assert_same_mesh(b, c, NORMALS_TOL, what="third request")

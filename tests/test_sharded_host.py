@@ -85,3 +85,53 @@ def test_s1_row_mask_formulation_equals_marching_scan():
   mod = importlib.util.module_from_spec(spec)
   spec.loader.exec_module(mod)
   assert mod.check(trials=24, seed=7) == 24
+
+
+def test_native_slab_range_matches_python(build_all):
+  """zm_slab_range (the partition the native multi-GPU step uses, pure host arithmetic -- callable without a GPU) cuts
+  the volume exactly like zmesh_b200.sharded.slab_planes."""
+  import ctypes as C
+  from zmesh_b200 import _lib
+  from zmesh_b200.sharded import slab_planes
+  lib = _lib.load()
+  for full in (2, 5, 64, 513, 2048):
+    for close in (False, True):
+      ncube = full + (2 if close else 0) - 1
+      for world in (1, 2, 3, 8):
+        for rank in range(world):
+          slab, lo, hi = _lib.zm_slab(), C.c_uint64(0), C.c_uint64(0)
+          rc = lib.zm_slab_range(full, int(close), rank, world, C.byref(slab), C.byref(lo), C.byref(hi))
+          if world > ncube:
+            assert rc != 0
+            continue
+          assert rc == 0
+          cube_lo, cube_hi, in_lo, in_hi, last = slab_planes(full, close, rank, world)
+          assert (slab.cube_lo, slab.cube_hi, lo.value, hi.value, bool(slab.last)) == (cube_lo, cube_hi, in_lo, in_hi, last)
+          assert slab.full_extent == full and slab.buf_lo == in_lo
+
+
+def test_multi_device_assembly_is_concatenation():
+  """Host logic of Mesher(devices=[...]): a label's mesh is its per-device parts concatenated in device order (face
+  indices are already cross-device), empty parts are skipped, the id is set."""
+  from zmesh_b200 import Mesh
+  from zmesh_b200.multi import MultiDeviceMesher
+  m = MultiDeviceMesher.__new__(MultiDeviceMesher)
+  a = Mesh(np.arange(6, dtype=np.float32).reshape(2, 3), np.array([[0, 1, 2]], np.uint32), None)
+  b = Mesh(np.arange(6, 9, dtype=np.float32).reshape(1, 3), np.array([[2, 1, 0], [0, 2, 1]], np.uint32), None)
+  out = m._assemble(42, [a, Mesh(), b])
+  assert out.id == 42 and out.vertices.shape == (3, 3) and out.faces.tolist() == [[0, 1, 2], [2, 1, 0], [0, 2, 1]]
+  assert np.array_equal(out.vertices, np.arange(9, dtype=np.float32).reshape(3, 3)) and out.normals is None
+  a.normals, b.normals = np.ones((2, 3)), np.zeros((1, 3))
+  assert m._assemble(1, [a, b]).normals.shape == (3, 3)
+  assert m._assemble(7, [Mesh(), Mesh()]).empty() and m._assemble(7, []).id == 7
+  assert m._assemble(9, [b]).faces.shape == (2, 3)
+
+
+def test_mesher_devices_argument_dispatch():
+  """Mesher(voxel_res, devices=[d]) is a plain Mesher on d; only lists of two or more devices take the multi-device class
+  (constructing either needs a GPU: here only the dispatch of __new__ is checked)."""
+  import inspect
+  from zmesh_b200 import Mesher
+  sig = inspect.signature(Mesher.__init__)
+  assert list(sig.parameters)[1:] == ["voxel_res", "device", "devices"]
+  assert sig.parameters["device"].default == -1 and sig.parameters["devices"].default is None
