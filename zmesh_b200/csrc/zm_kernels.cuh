@@ -16,23 +16,24 @@
 //     so a lookup is two shared loads and a popc;  perm[g] = index of the vertex inside its
 //     label's vertex list.
 //
-// Pass 1 (k_classify, the only kernel that reads the label volume): persistent CTAs walk the tiles
-// of 32 x 8 x 8 voxels; the (+1 halo) label region is staged in shared memory by TMA
-// (cp.async.bulk.tensor.3d, zero fill outside the volume = the `close` border for free) and the
-// load of the CTA's next tile is issued as soon as the current region is dead.  A tile whose
-// whole region is one value is recognised with 16-byte compares and costs nothing else.  Active
-// voxels are compacted, distinct labels of each cube enumerated, per-(tile,label) counts kept in a
-// shared-memory table with warp-aggregated atomics, one global reservation per (tile,label).
-// Outputs, all label-free:
+// Pass 1 (k_classify, the only kernel that reads the label volume): one CTA per tile of 32 x 8 x 8 voxels; the
+// (+1 halo) label region is staged in shared memory by TMA (cp.async.bulk.tensor.3d, zero fill outside the volume =
+// the `close` border for free), the region of the tile one layer up is pulled into L2.  A tile whose whole region is
+// one value is recognised with 16-byte compares and costs nothing else.  A tile with exactly two labels takes the
+// bit-parallel path (tile_body_k2: one mask per staged row, everything else is arithmetic on whole rows); the general
+// path compacts the active voxels, enumerates the distinct labels of each cube and keeps per-(tile,label) counts in a
+// shared-memory table; tiles that overflow the per-tile staging are redone by the MODE 1 launch.  One global
+// reservation per (tile,label).  Outputs, all label-free:
 //   rowinfo[row segment], perm[g] (4 B/vertex), vinfo[g] (4 B/vertex: voxel-in-tile, slot,
 //   tile-local label index), rec[] (8 B per (label,cube) pair: voxel-in-tile | case | tile-local
 //   label index, first face row inside the (tile,label) block), tl[] (per (tile,label): label slot
 //   + face base), hdr[] work list of the non-empty tiles.
 // Scan (k_scan_*) turns per-label counts into per-label output offsets; k_tl_fixup folds them into
-// tl[].  Pass 2 (k_emit) never touches labels again: persistent CTAs walk the work list, stage the
+// tl[].  Pass 2 (k_emit) never touches labels again: persistent warp-specialised CTAs walk the work list, stage the
 // rowinfo region of a tile with one TMA load, and write faces (uint32 triples, one triangle per
-// lane) [+ face normals accumulation] and float32 vertices in the final form
-// fl32(fl32(fl32(res*k) [+ off]) / 2).
+// lane) [+ face normals: one 16-byte vector atomic per corner] and float32 vertices in the final form
+// fl32(fl32(fl32(res*k) [+ off]) / 2).  k_pack_precomputed lays out the Neuroglancer objects; k_export_directory /
+// k_import_directories / k_export_plane / k_import_plane_normals are the device ends of the multi-GPU exchanges.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
