@@ -38,6 +38,20 @@ def main():
     blob[f"{name}/precomputed"] = np.frombuffer(m.to_precomputed(), dtype=np.uint8)
     blob[f"{name}/ply"] = np.frombuffer(bytes(m.to_ply()), dtype=np.uint8)
     blob[f"{name}/obj"] = np.frombuffer(m.to_obj() if isinstance(m.to_obj(), bytes) else m.to_obj().encode("utf8"), dtype=np.uint8)
+  # host-side clean-up utilities (zmesh/mesh.py:117-226) on a seeded mesh with duplicate vertices, degenerate and
+  # repeated faces
+  rng = np.random.default_rng(11)
+  v = rng.integers(0, 4, size=(40, 3)).astype(np.float32)
+  f = rng.integers(0, 40, size=(90, 3)).astype(np.uint32)
+  n = rng.random((40, 3)).astype(np.float32)
+  blob["messy/v"], blob["messy/f"], blob["messy/n"] = v, f, n
+  for op in ("remove_unreferenced_vertices", "remove_degenerate_faces", "consolidate"):
+    r = getattr(Mesh(v, f, n), op)()
+    blob[f"messy/{op}/v"], blob[f"messy/{op}/f"] = r.vertices, r.faces
+    blob[f"messy/{op}/n"] = np.zeros((0, 3), np.float32) if r.normals is None else r.normals
+  v2 = (rng.random((40, 3)) * 3).astype(np.float32)
+  r = Mesh(v2, f, None).merge_close_vertices(0.8)
+  blob["messy/v2"], blob["messy/merge/v"], blob["messy/merge/f"] = v2, r.vertices, r.faces
   np.savez_compressed(os.path.join(ROOT, "tests", "golden", "codec_golden.npz"), **blob)
   print("wrote", len(blob), "arrays")
 

@@ -91,6 +91,78 @@ class Mesh:
     faces = np.concatenate([m.faces.astype(index_t, copy=False) + index_t(starts[i]) for i, m in enumerate(meshes)])
     return cls(verts, faces, None, id=id)
 
+  # -- host-side clean-up utilities (zmesh/mesh.py:117-226; plain numpy, results identical to the reference's) ---------
+  def remove_unreferenced_vertices(self) -> "Mesh":
+    """Drop the vertices no face refers to and renumber the faces (normals are not kept, as in the reference)."""
+    if self.empty():
+      return Mesh([], [], None)
+    used = np.zeros(len(self.vertices), dtype=bool)
+    used[self.faces] = True
+    new_index = np.cumsum(used) - 1
+    return Mesh(self.vertices[used], new_index[self.faces], None)
+
+  def remove_degenerate_faces(self) -> "Mesh":
+    """Drop faces that name a vertex twice, then faces that repeat another one up to the order of their corners (the
+    survivors come out in the lexicographic order of their sorted corner triples, as np.unique leaves them)."""
+    if self.empty():
+      return Mesh([], [], None)
+    f = self.faces
+    f = f[(f[:, 0] != f[:, 1]) & (f[:, 1] != f[:, 2]) & (f[:, 0] != f[:, 2])]
+    _, first = np.unique(np.sort(f, axis=1), axis=0, return_index=True)
+    return Mesh(self.vertices, f[first], self.normals, id=self.id)
+
+  def consolidate(self) -> "Mesh":
+    """Merge bit-identical vertices, drop duplicate and degenerate faces and unreferenced vertices; a new mesh."""
+    if self.empty():
+      return Mesh([], [], None)
+    verts, rep, inverse = np.unique(self.vertices, axis=0, return_index=True, return_inverse=True)
+    faces = np.unique(inverse.reshape(-1)[self.faces], axis=0)
+    normals = self.normals[rep] if self._has_normals() else None
+    return Mesh(verts, faces, normals, id=self.id).remove_degenerate_faces().remove_unreferenced_vertices()
+
+  def merge_close_vertices(self, radius: float = 1e-5) -> "Mesh":
+    """Merge vertices closer than `radius` (Euclidean); needs scipy."""
+    from scipy.spatial import cKDTree
+    if radius is None:
+      radius = np.inf
+    if radius <= 0:
+      raise ValueError("radius must be greater than zero: " + str(radius))
+    mesh = self.consolidate()
+    pairs = cKDTree(mesh.vertices).query_pairs(r=radius, p=2, eps=0, output_type="ndarray")
+    remap = np.arange(len(mesh.vertices), dtype=np.uint32)
+    remap[pairs[:, 1]] = pairs[:, 0]
+    mesh.faces = remap[mesh.faces]
+    return mesh.consolidate()
+
+  def dust(self, *args, **kwargs):
+    raise NotImplementedError("zmesh_b200 covers mesh extraction only (connected components / dust are out of scope)")
+
+  def largest_k(self, *args, **kwargs):
+    raise NotImplementedError("zmesh_b200 covers mesh extraction only (connected components / largest_k are out of scope)")
+
+  def save(self, filename: str):
+    """Write a .ply (binary little endian) or, for any other extension, a Wavefront .obj (zmesh/mesh.py:423-436)."""
+    with open(filename, "wb") as f:
+      f.write(self.to_ply() if filename.endswith(".ply") else self.to_obj())
+
+  @classmethod
+  def load(cls, filename: str) -> "Mesh":
+    """Read a .ply / .obj file written by save(), optionally gzip-compressed (.gz)."""
+    import gzip
+    name = filename
+    if name.endswith(".gz"):
+      with gzip.open(filename, "rb") as f:
+        binary = f.read()
+      name = name[:-3]
+    else:
+      with open(filename, "rb") as f:
+        binary = f.read()
+    if name.endswith(".ply"):
+      return cls.from_ply(binary)
+    if name.endswith(".obj"):
+      return cls.from_obj(binary)
+    raise ValueError(f"File format not supported: {filename}")
+
   # -- wire formats -----------------------------------------------------------------------------
   def to_precomputed(self) -> bytes:
     """Neuroglancer layout: uint32 Nv, Nv*3 float32, then uint32 face indices (no normals)."""
