@@ -135,3 +135,16 @@ def test_mesher_devices_argument_dispatch():
   sig = inspect.signature(Mesher.__init__)
   assert list(sig.parameters)[1:] == ["voxel_res", "device", "devices"]
   assert sig.parameters["device"].default == -1 and sig.parameters["devices"].default is None
+
+
+def test_two_label_path_equals_per_voxel_definition():
+  """Pure-Python restatement of k_classify's two-label path (tools/emulate_k2_path.py): slot planes, active-cube masks,
+  A's slot count, the number of records and every cube's corner masks follow from one 33-bit mask per staged row exactly
+  as the per-voxel definition gives them; boundary tiles, zero fill and slab shards included."""
+  import importlib.util
+  import os
+  from tests.conftest import ROOT
+  spec = importlib.util.spec_from_file_location("emulate_k2_path", os.path.join(ROOT, "tools", "emulate_k2_path.py"))
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  assert mod.check(trials=40, seed=5) >= 24
